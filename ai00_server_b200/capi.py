@@ -1,0 +1,100 @@
+"""ctypes binding of include/b200rwkv.h (the C-ABI shared library is the product; this file is
+only the Python-side loader used by tests/ and bench.py).
+
+The library is loaded from the package directory (built in-tree by ai00_server_b200.build);
+loading fails loudly if it is missing — there is no CPU or eager fallback for any entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200rwkv.so")
+
+OK = 0
+ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE = -1, -2, -3, -4
+OPTION_LAST, OPTION_FULL, OPTION_NONE = 0, 1, 2
+TP_HANDLE_BYTES = 128
+
+
+class Info(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "version", "num_layer", "num_emb", "num_hidden", "num_vocab", "num_head", "head_size",
+        "time_mix_adapter", "time_decay_adapter")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200rwkv error {code}: {msg}")
+        self.code = code
+
+
+# every symbol include/b200rwkv.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = [
+    ("b200rwkv_info_from_st", C.c_int32, [_P, C.c_size_t, C.POINTER(Info)]),
+    ("b200rwkv_create", C.c_int32, [_P, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    ("b200rwkv_create_tp", C.c_int32, [_P, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    ("b200rwkv_tp_export", C.c_int32, [_P, _P]),
+    ("b200rwkv_tp_connect", C.c_int32, [_P, _P]),
+    ("b200rwkv_destroy", None, [_P]),
+    ("b200rwkv_get_info", C.c_int32, [_P, C.POINTER(Info)]),
+    ("b200rwkv_infer", C.c_int32, [_P, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    ("b200rwkv_state_shape", C.c_int32, [_P, C.POINTER(C.c_int64 * 4)]),
+    ("b200rwkv_state_init", C.c_int32, [_P, _P]),
+    ("b200rwkv_state_load", C.c_int32, [_P, C.c_int32, _P]),
+    ("b200rwkv_state_back", C.c_int32, [_P, C.c_int32, _P]),
+    ("b200rwkv_state_read", C.c_int32, [_P, C.c_int32, C.POINTER(C.c_uint64)]),
+    ("b200rwkv_state_write", C.c_int32, [_P, C.c_int32, C.c_uint64]),
+    ("b200rwkv_state_free", C.c_int32, [_P, C.c_uint64]),
+    ("b200rwkv_softmax", C.c_int32, [_P, C.c_int32, _P, _P]),
+    ("b200rwkv_host_alloc", C.c_int32, [C.c_size_t, C.POINTER(_P)]),
+    ("b200rwkv_host_free", None, [_P]),
+    ("b200rwkv_bench_decode", C.c_int32, [_P, C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]),
+    ("b200rwkv_profile_step", C.c_int32, [_P, C.c_int32, _P, _P, C.POINTER(C.c_float * 4), C.POINTER(C.c_int32 * 4), C.POINTER(C.c_int64)]),
+    ("b200rwkv_last_hidden", C.c_int32, [_P, _P, C.c_size_t]),
+    ("b200rwkv_debug_read", C.c_int32, [_P, C.c_char_p, _P, C.c_size_t]),
+    ("b200rwkv_last_error", C.c_char_p, [_P]),
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libb200rwkv.so; raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -m ai00_server_b200.build` "
+                              "(there is no CPU fallback for the RWKV engine)")
+        l = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(l, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(code: int, engine=None):
+    if code < 0:
+        msg = lib().b200rwkv_last_error(engine)
+        raise B200Error(code, msg.decode("utf-8", "replace") if msg else "")
+    return code
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def info_from_st(st: np.ndarray) -> dict:
+    st = np.ascontiguousarray(st, dtype=np.uint8)
+    out = Info()
+    check(lib().b200rwkv_info_from_st(ptr(st), st.size, C.byref(out)))
+    return out.as_dict()

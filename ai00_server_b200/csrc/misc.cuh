@@ -1,0 +1,82 @@
+// Softmax over the vocabulary, state layout transforms, small conversion kernels.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------
+// Row softmax (replaces `web_rwkv::runtime::softmax::softmax`, reference run.rs:1179).
+// One CTA per row; the row (256 KB at V = 65536) is read twice from L2 and written once.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) softmax_kernel(const float* __restrict__ in, float* __restrict__ out, int V) {
+    __shared__ float red[32];
+    const float* x = in + (size_t)blockIdx.x * V;
+    float* y = out + (size_t)blockIdx.x * V;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, x[i]);
+    mx = block_max(mx, red);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(x[i] - mx);
+    s = block_sum(s, red);
+    const float inv = 1.0f / s;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) y[i] = expf(x[i] - mx) * inv;
+}
+
+// ---------------------------------------------------------------------------------------
+// State import / export between the API layout and the device layout.
+// API (web-rwkv shape [C, N+2, L, 1], x fastest; reference run.rs:987, lib.rs:267-272;
+// SURVEY.md App. C) per slot: api[l][row][c], row 0 = time-mix shift, rows 1..N = WKV with
+// row 1+i, col h*N+j <-> S[l,h][i][j], row N+1 = channel-mix shift.
+// Device: att_shift[l][slot][c], ffn_shift[l][slot][c], wkv[l][slot][h][value][key].
+// v5/v6: S[i=key][j=value]  -> M[value=j][key=i]   (transpose)
+// v7:    S[i=value][j=key]  -> M[value=i][key=j]
+// `h0`/`Hl`: first global head and head count held by this rank (tensor parallel).
+// ---------------------------------------------------------------------------------------
+struct StateXform {
+    float* api;          // [L][N+2][C] staging in HBM
+    float* att_shift;    // [L][S][C]
+    float* ffn_shift;    // [L][S][C]
+    float* wkv;          // [L][S][Hl][64][64]
+    int L, C, S, Hl, h0, slot, transpose;
+};
+
+template <bool IMPORT>
+__global__ void state_xform_kernel(const StateXform p) {
+    const int N = 64;
+    const size_t per_layer = (size_t)(N + 2) * p.C;
+    const size_t total = (size_t)p.L * per_layer;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int l = (int)(i / per_layer);
+        const size_t r = i - (size_t)l * per_layer;
+        const int row = (int)(r / p.C);
+        const int c = (int)(r - (size_t)row * p.C);
+        float* dev;
+        if (row == 0) dev = p.att_shift + ((size_t)l * p.S + p.slot) * p.C + c;
+        else if (row == N + 1) dev = p.ffn_shift + ((size_t)l * p.S + p.slot) * p.C + c;
+        else {
+            const int hg = c / N, j = c % N, ii = row - 1;
+            const int hl = hg - p.h0;
+            if (hl < 0 || hl >= p.Hl) {
+                if (!IMPORT) p.api[i] = 0.f;
+                continue;
+            }
+            const int val = p.transpose ? j : ii, key = p.transpose ? ii : j;
+            dev = p.wkv + ((((size_t)l * p.S + p.slot) * p.Hl + hl) * N + val) * N + key;
+        }
+        if (IMPORT) *dev = p.api[i];
+        else p.api[i] = *dev;
+    }
+}
+
+__global__ void f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n, float scale, float bias) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = __half2float(src[i]) * scale + bias;
+}
+
+// v5 static decay: w = exp(-exp(time_decay))
+__global__ void decay_table_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = expf(-expf(__half2float(src[i])));
+}
+
+}  // namespace b200

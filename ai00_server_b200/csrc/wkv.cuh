@@ -1,0 +1,200 @@
+// WKV recurrences: v5 / v6 multi-head state update and v7 delta rule, fused with the per-head
+// GroupNorm (eps 64e-5), the v7 bonus term and the output gate.
+//
+// Replaces web-rwkv's `time_mix_v5` / `time_mix_v6` / `time_mix_v7` + `group_norm` WGSL
+// dispatches under `Runtime::infer` (reference run.rs:1143; SURVEY.md §2.2 K6/K6'/K7, math in
+// App. A / App. B).
+//
+// One CTA per (head, active slot).  The 64x64 f32 head state (16 KB) lives in HBM as
+// M[value][key] for every version (v6's S[key][value] is stored transposed; the API layout is
+// restored by the state import/export kernels), so that
+//   * each thread owns a 4(value) x 4(key) patch: 4 coalesced 16-byte loads, rows read as full
+//     256-byte runs, 16 KB per CTA in flight, ~5 CTAs per SM;
+//   * every reduction of the recurrence runs over the KEY index = across the 16 lanes of a
+//     half-warp -> pure shuffles, no shared-memory round trip:
+//       v5/v6: out[v] = sum_k r[k] * (u[k] k[k] v[v] + M[v][k]);  M[v][k] = k[k] v[v] + w[k] M[v][k]
+//       v7:    sa[v]  = sum_k M[v][k] * (-kk[k]);
+//              M[v][k] = M[v][k] w[k] + sa[v] (kk[k] a[k]) + v[v] k[k];   out[v] = sum_k M[v][k] r[k]
+//   * state is read once and written once per step (streaming cache hints), the recurrence
+//     loops over the slot's tokens with the state in registers (prefill chunks).
+// Output: f16( GroupNorm(out) [+ bonus] * gate ) written straight into the A16 operand of the
+// output projection.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int WKV_THREADS = 256;
+constexpr int WKV_N = 64;            // head size (all supported RWKV v5/v6/v7 models)
+constexpr float GN_EPS = 64e-5f;
+
+struct WkvParams {
+    int version;            // 5, 6, 7
+    int ld;                 // row stride of r/k/v/g/w/a/nu (floats) = local channels
+    MetaView meta;
+    float* state;           // [S][H][64][64] this layer, M[value][key]
+    int H;                  // local heads
+    const float* r;
+    const float* k;
+    const float* v;
+    const float* g;         // v5/v6: silu(gate proj); v7: gate LoRA output
+    const float* w;         // [T, ld] decay in (0,1) (v6/v7); null for v5
+    const float* w_static;  // [ld] v5 decay exp(-exp(time_decay))
+    const float* u;         // [ld] v5/v6 time_first
+    const float* lnx_w;
+    const float* lnx_b;
+    // v7
+    const float* a;         // [T, ld] in-context learning rate
+    const float* nu;        // [T, ld] value-residual gate (layers > 0)
+    float* v_first;         // [T, ld] layer 0 writes, later layers read
+    int layer0;
+    const float* k_k;
+    const float* k_a;
+    const float* r_k;
+    __half* out;            // A16 [T, ld]
+    int kq_tile;
+};
+
+template <int VER>
+__global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant__ WkvParams p) {
+    __shared__ float s_r[WKV_N], s_k[WKV_N], s_v[WKV_N], s_w[WKV_N], s_b[WKV_N], s_o[WKV_N];
+    __shared__ float s_red[4];
+    pdl_launch_dependents();
+    const int si = blockIdx.y;
+    const int h = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int ig = tid >> 4;           // value rows 4*ig .. 4*ig+3
+    const int j4 = tid & 15;           // key cols  4*j4 .. 4*j4+3
+
+    pdl_wait();
+    if (si >= p.meta.nslots()) return;
+    const int slot = p.meta.slot_id()[si];
+    const int t0 = p.meta.slot_start()[si];
+    const int nt = p.meta.slot_count()[si];
+
+    float* M = p.state + ((size_t)slot * p.H + h) * (WKV_N * WKV_N);
+    float4 m[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m[e] = __ldcs(reinterpret_cast<const float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4));
+
+    const int ch = h * WKV_N;          // channel base of this head
+    float u4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (VER != 7) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) u4[f] = p.u[ch + j4 * 4 + f];
+    }
+
+    for (int tt = 0; tt < nt; ++tt) {
+        const int t = t0 + tt;
+        const size_t row = (size_t)t * p.ld + ch;
+        // ---- per-token head vectors -> shared ----
+        if (tid < WKV_N) {
+            const int c = tid;
+            float r = p.r[row + c], k = p.k[row + c], v = p.v[row + c];
+            float w;
+            if (VER == 5) w = p.w_static[ch + c];
+            else w = p.w[row + c];
+            if (VER == 7) {
+                const float a = p.a[row + c];
+                float kk = k * p.k_k[ch + c];
+                // l2 norm over the head: two warps
+                float ss = warp_sum(kk * kk);
+                if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+                asm volatile("bar.sync 2, 64;" ::: "memory");
+                ss = s_red[0] + s_red[1];
+                kk = kk / fmaxf(sqrtf(ss), 1e-12f);
+                k = k * (1.f + (a - 1.f) * p.k_a[ch + c]);
+                if (p.layer0) p.v_first[row + c] = v;
+                else v = v + (p.v_first[row + c] - v) * p.nu[row + c];
+                float bonus = warp_sum(r * k * p.r_k[ch + c]);
+                if ((tid & 31) == 0) s_red[2 + (tid >> 5)] = bonus;
+                s_b[c] = kk * a;        // kk (.) a
+                s_o[c] = -kk;           // reuse s_o as -kk until the output phase
+            }
+            s_r[c] = r; s_k[c] = k; s_v[c] = v; s_w[c] = w;
+        }
+        __syncthreads();
+
+        float rr[4], kk_[4], ww[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) { rr[f] = s_r[j4 * 4 + f]; kk_[f] = s_k[j4 * 4 + f]; ww[f] = s_w[j4 * 4 + f]; }
+        float o[4];
+        if (VER != 7) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float vv = s_v[ig * 4 + e];
+                float* me = reinterpret_cast<float*>(&m[e]);
+                float acc = 0.f;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const float kv = kk_[f] * vv;
+                    acc += rr[f] * (u4[f] * kv + me[f]);
+                    me[f] = kv + ww[f] * me[f];
+                }
+                o[e] = acc;
+            }
+        } else {
+            float nk[4], ka[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) { nk[f] = s_o[j4 * 4 + f]; ka[f] = s_b[j4 * 4 + f]; }
+            float sa[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float* me = reinterpret_cast<const float*>(&m[e]);
+                sa[e] = (me[0] * nk[0] + me[1] * nk[1]) + (me[2] * nk[2] + me[3] * nk[3]);
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sa[e] += __shfl_xor_sync(0xffffffffu, sa[e], off);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float vv = s_v[ig * 4 + e];
+                float* me = reinterpret_cast<float*>(&m[e]);
+                float acc = 0.f;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    me[f] = me[f] * ww[f] + sa[e] * ka[f] + vv * kk_[f];
+                    acc += me[f] * rr[f];
+                }
+                o[e] = acc;
+            }
+        }
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], off);
+        __syncthreads();               // all reads of s_o (-kk) done before it is overwritten
+        if (j4 == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s_o[ig * 4 + e] = o[e];
+        }
+        __syncthreads();
+
+        // ---- GroupNorm over the head + gate, warp 0: 2 channels per lane ----
+        if (tid < 32) {
+            const float x0 = s_o[tid], x1 = s_o[tid + 32];
+            const float mean = warp_sum(x0 + x1) * (1.f / WKV_N);
+            const float d0 = x0 - mean, d1 = x1 - mean;
+            const float var = warp_sum(d0 * d0 + d1 * d1) * (1.f / WKV_N);
+            const float rstd = 1.0f / sqrtf(var + GN_EPS);
+            float y0 = d0 * rstd * p.lnx_w[ch + tid] + p.lnx_b[ch + tid];
+            float y1 = d1 * rstd * p.lnx_w[ch + tid + 32] + p.lnx_b[ch + tid + 32];
+            if (VER == 7) {
+                const float bonus = s_red[2] + s_red[3];
+                y0 += bonus * s_v[tid];
+                y1 += bonus * s_v[tid + 32];
+            }
+            y0 *= p.g[row + tid];
+            y1 *= p.g[row + tid + 32];
+            p.out[a16_index(t, ch + tid, p.kq_tile)] = f2h_sat(y0);
+            p.out[a16_index(t, ch + tid + 32, p.kq_tile)] = f2h_sat(y1);
+        }
+        __syncthreads();               // shared vectors are rewritten by the next token
+    }
+
+#pragma unroll
+    for (int e = 0; e < 4; ++e) __stcs(reinterpret_cast<float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4), m[e]);
+}
+
+}  // namespace b200

@@ -1,0 +1,245 @@
+"""Host-side mirror of the web-rwkv interface that crates/ai00-core consumes, over the C ABI.
+
+The reference's host code is Rust (crates/ai00-core/src/run.rs, lib.rs) and no Rust toolchain
+exists in this image, so the shim that would live in ai00-core is specified in INTEGRATION.md
+and mirrored here 1:1 in Python for the parity tests and bench.py: same names, argument
+meaning and error behaviour as the trait objects the reference holds:
+
+  RnnOption / RnnInputBatch / RnnInput / RnnOutputBatch   run.rs:25, 1121-1136, 1146
+  Runtime.infer(input) -> (input, output)                   run.rs:1143
+  State.{init, load, back, read, write}                     run.rs:477, 1099-1107
+  softmax(list of [V] tensors)                              run.rs:1179
+  Loader.info                                               lib.rs:587
+  ModelBuilder(...).build() + Bundle(model, max_batch)      lib.rs:484-497
+
+Every method calls straight into libb200rwkv.so; nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+
+class RnnOption(enum.IntEnum):
+    Last = capi.OPTION_LAST
+    Full = capi.OPTION_FULL
+
+
+@dataclass
+class RnnInputBatch:
+    tokens: list = field(default_factory=list)
+    option: RnnOption = RnnOption.Last
+
+
+@dataclass
+class RnnInput:
+    batches: list
+    token_chunk_size: int
+
+    def num_token(self) -> int:
+        return sum(len(b.tokens) for b in self.batches)
+
+
+@dataclass
+class RnnOutputBatch:
+    """`RnnOutputBatch(TensorCpu<f32>)`: [rows, V]; empty when the slot produced nothing."""
+    data: np.ndarray
+
+    def is_empty(self) -> bool:
+        return self.data.shape[0] == 0
+
+
+class Loader:
+    @staticmethod
+    def info(st: np.ndarray) -> dict:
+        return capi.info_from_st(st)
+
+
+class TensorGpu:
+    """Device-side state snapshot handle (`TensorGpu<f32, ReadWrite>` at run.rs:1104-1108)."""
+
+    def __init__(self, model: "Model", snap_id: int):
+        self._model, self.id = model, snap_id
+
+    def free(self):
+        if self.id:
+            capi.check(capi.lib().b200rwkv_state_free(self._model._h, self.id), self._model._h)
+            self.id = 0
+
+
+class State:
+    def __init__(self, model: "Model"):
+        self._m = model
+
+    def shape(self):
+        s = (C.c_int64 * 4)()
+        capi.check(capi.lib().b200rwkv_state_shape(self._m._h, C.byref(s)), self._m._h)
+        return tuple(s)
+
+    def _numel(self):
+        s = self.shape()
+        return int(s[0] * s[1] * s[2] * s[3])
+
+    def _np_shape(self):
+        c, r, l, _ = self.shape()
+        return (int(l), int(r), int(c))        # numpy C-order view of web-rwkv [C, N+2, L, 1]
+
+    def init(self) -> np.ndarray:
+        out = np.empty(self._np_shape(), np.float32)
+        capi.check(capi.lib().b200rwkv_state_init(self._m._h, capi.ptr(out)), self._m._h)
+        return out
+
+    def load(self, tensor: np.ndarray, batch: int) -> None:
+        t = np.ascontiguousarray(tensor, dtype=np.float32)
+        if t.size != self._numel():
+            raise capi.B200Error(capi.ERR_INVALID, "state tensor has the wrong number of elements")
+        capi.check(capi.lib().b200rwkv_state_load(self._m._h, batch, capi.ptr(t)), self._m._h)
+
+    def back(self, batch: int) -> np.ndarray:
+        out = np.empty(self._np_shape(), np.float32)
+        capi.check(capi.lib().b200rwkv_state_back(self._m._h, batch, capi.ptr(out)), self._m._h)
+        return out
+
+    def read(self, batch: int) -> TensorGpu:
+        sid = C.c_uint64(0)
+        capi.check(capi.lib().b200rwkv_state_read(self._m._h, batch, C.byref(sid)), self._m._h)
+        return TensorGpu(self._m, sid.value)
+
+    def write(self, tensor: TensorGpu, batch: int) -> None:
+        capi.check(capi.lib().b200rwkv_state_write(self._m._h, batch, tensor.id), self._m._h)
+
+
+class Runtime:
+    """`Arc<dyn Runtime<Rnn>>`.  `infer` consumes at most `token_chunk_size` tokens of the
+    input across slots and returns the remaining input with the per-slot outputs, exactly the
+    contract the batching shim loops on (run.rs:1134-1155)."""
+
+    def __init__(self, model: "Model"):
+        self._m = model
+
+    def infer(self, inp: RnnInput):
+        m = self._m
+        budget = max(1, inp.token_chunk_size)
+        slots, ntok, opts, toks, takes = [], [], [], [], []
+        for b, batch in enumerate(inp.batches):
+            if not batch.tokens or budget == 0:
+                takes.append(0)
+                continue
+            take = min(len(batch.tokens), budget)
+            budget -= take
+            takes.append(take)
+            finishes = take == len(batch.tokens)
+            slots.append(b)
+            ntok.append(take)
+            toks.extend(int(t) for t in batch.tokens[:take])
+            # Last only yields a row once the slot's tokens are exhausted
+            opts.append(int(RnnOption.Full) if batch.option == RnnOption.Full
+                        else (int(RnnOption.Last) if finishes else capi.OPTION_NONE))
+        rows = m.infer_raw(slots, ntok, toks, opts)
+        out = [RnnOutputBatch(np.zeros((0, m.info["num_vocab"]), np.float32)) for _ in inp.batches]
+        for s, r in zip(slots, rows):
+            out[s] = RnnOutputBatch(r)
+        rest = RnnInput([RnnInputBatch(list(b.tokens[t:]), b.option) for b, t in zip(inp.batches, takes)],
+                        inp.token_chunk_size)
+        return rest, out
+
+
+class Model:
+    """Owns one engine (`ModelBuilder...build_vN()` + `Bundle::new(model, max_batch)` +
+    `TokioRuntime::new(bundle)`, lib.rs:484-497)."""
+
+    def __init__(self, st: np.ndarray, max_batch: int = 8, token_chunk_size: int = 128, device: int = 0,
+                 precision: int = 0, rank: int = 0, world: int = 1):
+        st = np.ascontiguousarray(st, dtype=np.uint8)
+        h = C.c_void_p()
+        L = capi.lib()
+        capi.check(L.b200rwkv_create_tp(capi.ptr(st), st.size, device, max_batch, token_chunk_size, precision,
+                                        rank, world, C.byref(h)))
+        self._h = h
+        self.max_batch, self.token_chunk_size = max_batch, token_chunk_size
+        self.rank, self.world = rank, world
+        info = capi.Info()
+        capi.check(L.b200rwkv_get_info(self._h, C.byref(info)), self._h)
+        self.info = info.as_dict()
+        self.runtime = Runtime(self)
+        self.state = State(self)
+
+    def close(self):
+        if self._h:
+            capi.lib().b200rwkv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- raw call: one b200rwkv_infer ----
+    def infer_raw(self, slots, ntok, tokens, options, out: np.ndarray | None = None):
+        V = self.info["num_vocab"] // self.world
+        n = len(slots)
+        total = sum(nt if o == capi.OPTION_FULL else (1 if (o == capi.OPTION_LAST and nt > 0) else 0)
+                    for nt, o in zip(ntok, options))
+        if out is None:
+            out = np.empty((max(total, 1), V), np.float32)
+        a_slot = np.asarray(slots, np.int32)
+        a_ntok = np.asarray(ntok, np.int32)
+        a_tok = np.asarray(tokens, np.uint32)
+        a_opt = np.asarray(options, np.int32)
+        a_rows = np.zeros(max(n, 1), np.int32)
+        capi.check(capi.lib().b200rwkv_infer(self._h, n, capi.ptr(a_slot), capi.ptr(a_ntok), capi.ptr(a_tok),
+                                             capi.ptr(a_opt), capi.ptr(out), out.size, capi.ptr(a_rows)), self._h)
+        res, off = [], 0
+        for i in range(n):
+            r = int(a_rows[i])
+            res.append(out[off:off + r])
+            off += r
+        return res
+
+    def softmax(self, tensors):
+        """`softmax(&context, Vec<TensorCpu<f32>>)`: list of [V] rows in, list out."""
+        if not tensors:
+            return []
+        x = np.ascontiguousarray(np.stack([np.asarray(t, np.float32).reshape(-1) for t in tensors], 0))
+        y = np.empty_like(x)
+        capi.check(capi.lib().b200rwkv_softmax(self._h, x.shape[0], capi.ptr(x), capi.ptr(y)), self._h)
+        return [y[i] for i in range(y.shape[0])]
+
+    def last_hidden(self) -> np.ndarray:
+        Cc = self.info["num_emb"]
+        buf = np.empty((64, Cc), np.float32)
+        r = capi.lib().b200rwkv_last_hidden(self._h, capi.ptr(buf), buf.size)
+        capi.check(r, self._h)
+        return buf[:r]
+
+    def debug_read(self, name: str, rows: int = 64) -> np.ndarray:
+        buf = np.empty(rows * 65536, np.float32)
+        cols = capi.lib().b200rwkv_debug_read(self._h, name.encode(), capi.ptr(buf), buf.size)
+        capi.check(cols, self._h)
+        return buf[: rows * cols].reshape(rows, cols)
+
+    def bench_decode(self, slots, tokens: np.ndarray, warmup: int, steps: int, flush_l2: bool = False):
+        a_slot = np.asarray(slots, np.int32)
+        tok = np.ascontiguousarray(tokens, dtype=np.uint32)
+        assert tok.size == (warmup + steps) * len(slots)
+        ms = C.c_float(0)
+        launches = C.c_int64(0)
+        capi.check(capi.lib().b200rwkv_bench_decode(self._h, len(slots), capi.ptr(a_slot), capi.ptr(tok), warmup, steps,
+                                                    int(flush_l2), C.byref(ms), C.byref(launches)), self._h)
+        return ms.value, launches.value
+
+    def profile_step(self, slots, tokens):
+        a_slot = np.asarray(slots, np.int32)
+        tok = np.ascontiguousarray(tokens, dtype=np.uint32)
+        ms = (C.c_float * 4)()
+        ln = (C.c_int32 * 4)()
+        wb = C.c_int64(0)
+        capi.check(capi.lib().b200rwkv_profile_step(self._h, len(slots), capi.ptr(a_slot), capi.ptr(tok), C.byref(ms),
+                                                    C.byref(ln), C.byref(wb)), self._h)
+        return list(ms), list(ln), wb.value

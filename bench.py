@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py — decode tokens/s of the RWKV hot path on B200 (BASELINE.json metric).
+
+A "step" is one decode step of the whole model for every slot of the batch (one token per
+slot): the per-layer WKV recurrence + token shift + GroupNorm, all projections and the head.
+Workload at N=1: configs[2] of BASELINE.json, RWKV-6-World-7B shape, fp16 weights, batch 16,
+slots primed with a 128-token synthetic prompt (random-init weights of that architecture,
+there are no checkpoints offline).
+
+  value     tokens/s with token ids staged in HBM and logits left in HBM (CUDA events around
+            `steps` graph replays, b200rwkv_bench_decode)
+  e2e       the same metric through the reference-facing call (Runtime.infer ->
+            b200rwkv_infer): token ids copied H2D and all logits rows copied D2H every step
+  roofline  projection-GEMM kernel: algorithmic weight bytes per step / summed GEMM launch
+            durations (CUDA events on the engine's stream, un-graphed profiling pass)
+  cpu_baseline / --impl reference
+            the C/OpenMP oracle (oracle/rwkv_ref.c) on the host cores, same weights/tokens
+            (the reference's own web-rwkv+lavapipe path cannot be built here: no Rust, no Vulkan)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "decode tokens/s RWKV-6-World-7B fp16 batch=16"
+PRESET = os.environ.get("B200RWKV_BENCH_PRESET", "v6-7b")
+BATCH = int(os.environ.get("B200RWKV_BENCH_BATCH", "16"))
+PROMPT = int(os.environ.get("B200RWKV_BENCH_PROMPT", "128"))
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_tokens(n_steps: int, batch: int, vocab: int):
+    rng = np.random.default_rng(1234)
+    return rng.integers(1, min(vocab, 65530), size=(batch, n_steps), dtype=np.int64)
+
+
+def cpu_arm(weights, batch: int, steps: int, warmup: int, toks_bt: np.ndarray):
+    """Times the C/OpenMP oracle on the host cores: `steps` decode steps of the same workload."""
+    from ai00_server_b200 import build
+    from oracle import ref_c
+    if not os.path.exists(ref_c.LIB_PATH):
+        build.build_oracle()
+    rc = ref_c.RefC(weights, "f16")
+    st = rc.state_init(batch)
+    for i in range(warmup):
+        rc.decode_step(toks_bt[:, i % toks_bt.shape[1]], st)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        rc.decode_step(toks_bt[:, (warmup + i) % toks_bt.shape[1]], st)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, rc.num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=int(os.environ.get("B200RWKV_BENCH_CPU_STEPS", "6")))
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from ai00_server_b200 import synth
+    from oracle import rwkv_numpy as O          # only for parse_st of the cpu arm (checker side)
+    shape = synth.PRESETS[PRESET]
+    config = {"workload": f"{PRESET} decode, batch {BATCH} slots x 1 token/step, {PROMPT}-token synthetic prompt per slot",
+              "preset": PRESET, "batch": BATCH, "prompt_tokens": PROMPT, "parallelism": f"tp{world}",
+              "l2": "inputs larger than L2 (14.7 GB of weights streamed per step vs 126 MB L2), no flush"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        st = synth.make_st(shape, 0)
+        w = O.parse_st(st)
+        steps = max(1, min(args.steps, 8))
+        warm = 1
+        toks = make_tokens(steps + warm, BATCH, shape.V)
+        tps, ms, threads = cpu_arm(w, BATCH, steps, warm, toks)
+        line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
+                                 "sample": f"{steps} decode steps of the full workload (requested {args.steps}), C/OpenMP oracle; "
+                                           "reference web-rwkv/lavapipe path unbuildable here"},
+                "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch                                  # plumbing only: device selection + distributed barrier
+    from ai00_server_b200 import runtime
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank if world > 1 else 0
+
+    t_build = time.perf_counter()
+    st = synth.make_st(shape, 0)
+    model = runtime.Model(st, max_batch=BATCH, token_chunk_size=64, device=dev, rank=rank, world=world)
+    if world > 1:
+        from ai00_server_b200 import tp
+        tp.connect(model)
+    build_s = time.perf_counter() - t_build
+
+    n_steps = args.warmup + args.steps
+    toks = make_tokens(PROMPT + 2 * n_steps + 8, BATCH, shape.V)
+    slots = list(range(BATCH))
+    zero = model.state.init()
+    for s in slots:
+        model.state.load(zero, s)
+    # prime every slot with its prompt (prefill through the same path, untimed)
+    model.infer_raw(slots, [PROMPT] * BATCH, toks[:, :PROMPT].reshape(-1).tolist(), [2] * BATCH)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: resident inputs, graph replays, CUDA events ----
+    dec = np.ascontiguousarray(toks[:, PROMPT:PROMPT + n_steps].T).astype(np.uint32)       # [steps, B]
+    sampler = ClockSampler(dev)
+    barrier()
+    sampler.start()
+    ms, launches = model.bench_decode(slots, dec, args.warmup, args.steps)
+    barrier()
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = BATCH * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host tokens in, host logits out, every step, through Runtime.infer ----
+    V_local = shape.V // world
+    out = np.empty((BATCH, V_local), np.float32)
+    try:
+        tt = torch.from_numpy(out)
+        torch.cuda.cudart().cudaHostRegister(tt.data_ptr(), out.nbytes, 0)     # pinned host memory
+    except Exception:
+        pass
+    e2e_steps = args.steps
+    dec2 = toks[:, PROMPT + n_steps:PROMPT + n_steps + args.warmup + e2e_steps]
+    for i in range(args.warmup):
+        model.infer_raw(slots, [1] * BATCH, dec2[:, i].tolist(), [0] * BATCH, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        model.infer_raw(slots, [1] * BATCH, dec2[:, args.warmup + i].tolist(), [0] * BATCH, out=out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": BATCH * e2e_steps / e2e_s, "unit": "tokens/s", "ms_per_step": e2e_s / e2e_steps * 1e3,
+           "h2d_bytes_per_step": int((8 + 6 * 64 + 3 * BATCH) * 4), "d2h_bytes_per_step": int(out.nbytes),
+           "api": "runtime.Model.infer_raw -> b200rwkv_infer (host token ids in, host f32 logits out, wall clock)"}
+
+    if rank != 0:
+        model.close()
+        return
+
+    # ---- roofline of the dominant kernel (projection GEMM) ----
+    peaks, peak_src = read_peaks()
+    prof_ms = np.zeros(4)
+    prof_n = np.zeros(4, dtype=np.int64)
+    wbytes = 0
+    reps = 5
+    for i in range(reps + 1):
+        m4, n4, wbytes = model.profile_step(slots, dec[i % dec.shape[0]])
+        if i == 0:
+            continue                       # first un-graphed pass is cold
+        prof_ms += np.array(m4)
+        prof_n = np.array(n4)
+    prof_ms /= reps
+    gemm_gbs = wbytes / (prof_ms[0] * 1e-3) / 1e9 if prof_ms[0] > 0 else 0.0
+    alg_bytes = synth.algorithmic_bytes_per_step(shape, BATCH) / world
+    roofline = {"bound": "hbm", "kernel": "gemm_kernel<1> (all projection launches of one step)",
+                "achieved": gemm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gemm_gbs / peaks["hbm_gbs"],
+                "peak_source": f"MEASURED_PEAKS.json ({peak_src})", "traffic": None,
+                "algorithmic_bytes_per_step_gemm": int(wbytes), "gemm_ms_per_step": float(prof_ms[0]),
+                "gemm_launches_per_step": int(prof_n[0]),
+                "class_ms_per_step": {"gemm": float(prof_ms[0]), "wkv": float(prof_ms[1]), "ln_mix": float(prof_ms[2])},
+                "class_launches_per_step": {"gemm": int(prof_n[0]), "wkv": int(prof_n[1]), "ln_mix": int(prof_n[2])},
+                "step_algorithmic_bytes": int(alg_bytes),
+                "step_achieved_gbs": alg_bytes / (ms_per_step * 1e-3) / 1e9,
+                "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+
+    # ---- cpu baseline (rank 0, N=1 only) ----
+    cpu = None
+    if world == 1 and args.cpu_steps > 0:
+        w = O.parse_st(st)
+        ctoks = toks[:, PROMPT:PROMPT + args.cpu_steps + 1]
+        tps, cms, threads = cpu_arm(w, BATCH, args.cpu_steps, 1, ctoks)
+        cpu = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port", "ms_per_step": cms,
+               "sample": f"{args.cpu_steps} decode steps of the same workload on the host cores (C/OpenMP oracle, "
+                         "f16 weights, f32 math); reference web-rwkv/lavapipe path unbuildable here"}
+
+    line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "build_seconds": build_s}
+    print(json.dumps(line))
+    model.close()
+
+
+if __name__ == "__main__":
+    main()

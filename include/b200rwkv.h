@@ -1,0 +1,153 @@
+/* b200rwkv.h — C ABI of the B200-native RWKV inference engine.
+ *
+ * This is the drop-in boundary underneath crates/ai00-core: every entry point replaces one
+ * use of the `web-rwkv` crate at a call site of the reference (paths relative to the
+ * reference repository root).  The Rust shim that implements web-rwkv's `Runtime<Rnn>` /
+ * `State` traits on top of these functions is given in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative b200rwkv_status on failure; the message
+ *     is available from b200rwkv_last_error() (per engine, or thread-global when the engine
+ *     pointer is NULL / creation failed).  No exception crosses the boundary.
+ *   - all buffers are caller-owned plain host memory unless stated; nothing is retained after
+ *     the call returns (the `.st` image is only borrowed during b200rwkv_create).
+ *   - threading mirrors the reference: ONE task calls infer/state ops
+ *     (crates/ai00-core/src/run.rs:1232) and ONE task calls softmax (run.rs:1237); the engine
+ *     serialises each group with an internal mutex.
+ *   - there is no CPU fallback: creation fails if no sm_100 device is present.
+ */
+#ifndef B200RWKV_H
+#define B200RWKV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200rwkv_engine b200rwkv_engine;
+
+typedef enum {
+    B200RWKV_OK = 0,
+    B200RWKV_ERR_INVALID = -1,     /* bad argument / malformed .st */
+    B200RWKV_ERR_UNSUPPORTED = -2, /* model version or precision not supported */
+    B200RWKV_ERR_CUDA = -3,        /* CUDA failure: the engine is dead, reload it */
+    B200RWKV_ERR_STATE = -4        /* unknown slot / snapshot id */
+} b200rwkv_status;
+
+/* Mirror of web-rwkv `ModelInfo` as consumed at crates/ai00-core/src/lib.rs:587 and
+ * crates/ai00-core/src/run.rs:672 (fields `version`, `num_vocab` are read by the core). */
+typedef struct {
+    int32_t version;            /* 5, 6 or 7 */
+    int32_t num_layer;
+    int32_t num_emb;
+    int32_t num_hidden;
+    int32_t num_vocab;
+    int32_t num_head;
+    int32_t head_size;
+    int32_t time_mix_adapter;   /* v6 ddlerp LoRA rank */
+    int32_t time_decay_adapter; /* v6 decay / v7 w LoRA rank */
+} b200rwkv_info;
+
+/* RnnOption (crates/ai00-core/src/run.rs:25, used at run.rs:710-724, 812-822). */
+enum {
+    B200RWKV_OPTION_LAST = 0,
+    B200RWKV_OPTION_FULL = 1,
+    /* consume the tokens, emit no logits: what a shim passes for a Last slot whose token run is
+     * cut by token_chunk_size and continues in the next infer call (run.rs:1134-1145) */
+    B200RWKV_OPTION_NONE = 2
+};
+
+/* Replaces `Loader::info(&SafeTensors)` — crates/ai00-core/src/lib.rs:587,
+ * crates/ai00-server/src/api/file.rs:115.  Pure host code, no GPU needed. */
+int32_t b200rwkv_info_from_st(const uint8_t* st, size_t len, b200rwkv_info* out);
+
+/* Replaces `ModelBuilder::new(ctx, st).build_vN()` + `vN::Bundle::<f16>::new(model, max_batch)`
+ * + `TokioRuntime::<Rnn>::new(bundle)` — crates/ai00-core/src/lib.rs:484-515.
+ * `device` is the CUDA ordinal (the reference's adapter selection, lib.rs:351-368).
+ * precision: 0 = fp16 weights (f32 accumulate/state/logits); 1 (fp32) is rejected with
+ * B200RWKV_ERR_UNSUPPORTED. */
+int32_t b200rwkv_create(const uint8_t* st, size_t len, int32_t device, int32_t max_batch,
+                        int32_t token_chunk_size, int32_t precision, b200rwkv_engine** out);
+
+/* Tensor-parallel construction, one process per GPU (head / column parallel).
+ * Every rank calls create_tp with the same model, then exchanges the opaque handle blobs
+ * (b200rwkv_tp_export on each rank, all-gathered by the host over any side channel) and
+ * passes all `world` blobs, rank-ordered, to b200rwkv_tp_connect.  After that every API call
+ * is SPMD: all ranks make the same call with the same arguments. */
+#define B200RWKV_TP_HANDLE_BYTES 128
+int32_t b200rwkv_create_tp(const uint8_t* st, size_t len, int32_t device, int32_t max_batch,
+                           int32_t token_chunk_size, int32_t precision, int32_t rank, int32_t world,
+                           b200rwkv_engine** out);
+int32_t b200rwkv_tp_export(b200rwkv_engine*, uint8_t handle_out[B200RWKV_TP_HANDLE_BYTES]);
+int32_t b200rwkv_tp_connect(b200rwkv_engine*, const uint8_t* handles /* world * HANDLE_BYTES */);
+
+/* Dropping the `Arc<dyn Runtime>` (crates/ai00-core/src/lib.rs:600,654). */
+void b200rwkv_destroy(b200rwkv_engine*);
+
+int32_t b200rwkv_get_info(b200rwkv_engine*, b200rwkv_info* out);
+
+/* Replaces `Runtime::infer(RnnInput)` — crates/ai00-core/src/run.rs:1143 — for one
+ * `RnnInput`: a ragged batch of `nslot` entries; entry i feeds `ntok[i]` tokens
+ * (tokens + sum(ntok[0..i])) to state slot `slot[i]` with RnnOption `option[i]`.
+ * All tokens are consumed (internally in chunks of at most token_chunk_size, the policy
+ * web-rwkv applies across calls at run.rs:1134-1145).  Logits rows (num_vocab f32 each) are
+ * written contiguously to `logits_out` in entry order: 1 row for LAST (0 if ntok[i]==0),
+ * ntok[i] rows for FULL, none for NONE; rows_out[i] receives the row count of entry i
+ * (== RnnOutputBatch being empty or not, run.rs:1146-1155).  `logits_cap` is in floats. */
+int32_t b200rwkv_infer(b200rwkv_engine*, int32_t nslot, const int32_t* slot, const int32_t* ntok,
+                       const uint32_t* tokens, const int32_t* option, float* logits_out,
+                       size_t logits_cap, int32_t* rows_out);
+
+/* `State` trait object — crates/ai00-core/src/lib.rs:399,494; uses at run.rs:477,1099-1107.
+ * The host-visible state of one slot is an f32 tensor of web-rwkv shape [C, N+2, L, 1]
+ * (x fastest; run.rs:987): row 0 time-mix shift, rows 1..N WKV, row N+1 channel-mix shift. */
+int32_t b200rwkv_state_shape(b200rwkv_engine*, int64_t shape[4]);
+int32_t b200rwkv_state_init(b200rwkv_engine*, float* out);                          /* State::init  */
+int32_t b200rwkv_state_load(b200rwkv_engine*, int32_t slot, const float* in);        /* State::load  */
+int32_t b200rwkv_state_back(b200rwkv_engine*, int32_t slot, float* out);             /* State::back  */
+int32_t b200rwkv_state_read(b200rwkv_engine*, int32_t slot, uint64_t* snapshot_id);  /* State::read  (device copy) */
+int32_t b200rwkv_state_write(b200rwkv_engine*, int32_t slot, uint64_t snapshot_id);  /* State::write */
+int32_t b200rwkv_state_free(b200rwkv_engine*, uint64_t snapshot_id);                 /* drop TensorGpu */
+
+/* Replaces `web_rwkv::runtime::softmax::softmax(&context, Vec<TensorCpu<f32>>)` —
+ * crates/ai00-core/src/run.rs:1179.  in/out: [rows, num_vocab] f32. */
+int32_t b200rwkv_softmax(b200rwkv_engine*, int32_t rows, const float* in, float* out);
+
+/* Pinned host memory for logits / state buffers (full-rate DMA); optional. */
+int32_t b200rwkv_host_alloc(size_t bytes, void** out);
+void b200rwkv_host_free(void* p);
+
+/* Measurement hook used by bench.py for the kernel-resident number: runs `warmup + steps`
+ * decode steps (one token per listed slot per step) with token ids staged in HBM beforehand,
+ * no host<->device traffic inside the timed region; returns CUDA-event milliseconds for the
+ * `steps` timed steps, the number of kernel launches in that region, and the device time
+ * spent in the projection GEMM kernels (sum of per-launch event durations, measured in a
+ * separate un-graphed pass of `gemm_probe_steps` steps; 0 to skip). */
+int32_t b200rwkv_bench_decode(b200rwkv_engine*, int32_t nslot, const int32_t* slot,
+                              const uint32_t* tokens /* [(warmup+steps) * nslot] */, int32_t warmup,
+                              int32_t steps, int32_t flush_l2, float* ms_out, int64_t* launches_out);
+
+/* Per-kernel-class device time of ONE un-graphed decode step, CUDA events around every launch
+ * on the engine's stream.  classes: 0 = projection GEMMs, 1 = WKV, 2 = LN/mix/embed, 3 = other.
+ * ms[4], launches[4], and algorithmic weight bytes streamed by the GEMM launches. */
+int32_t b200rwkv_profile_step(b200rwkv_engine*, int32_t nslot, const int32_t* slot,
+                              const uint32_t* tokens, float ms[4], int32_t launches[4],
+                              int64_t* gemm_weight_bytes);
+
+/* Optional copy of the residual stream after the last layer for every token of the most
+ * recent infer call ([T, C] f32) — the hidden state the documented embeddings route returns
+ * (reference docs/doc-api/openai.md:376-437).  Returns the number of rows written. */
+int32_t b200rwkv_last_hidden(b200rwkv_engine*, float* out, size_t cap);
+
+/* Test aid: copy a named internal activation buffer of the most recent step to the host as f32
+ * row-major; returns the column count (negative status on error).  Not on the product path. */
+int32_t b200rwkv_debug_read(b200rwkv_engine*, const char* name, float* out, size_t cap);
+
+const char* b200rwkv_last_error(b200rwkv_engine*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RWKV_H */

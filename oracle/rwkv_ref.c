@@ -1,0 +1,247 @@
+/* CPU oracle, C/OpenMP restatement of the RWKV v5/v6 decode step (one token per slot).
+ *
+ * TEST INFRASTRUCTURE ONLY: used by tests/ (cross-checked against oracle/rwkv_numpy.py and the
+ * committed goldens) and as bench.py's `cpu_baseline` / `--impl reference` arm, where it stands
+ * in for the reference's own CPU path (web-rwkv on lavapipe), which cannot be built in this image
+ * (no Rust toolchain, no Vulkan loader).  PARITY UNPINNED: the reference
+ * holds no golden vectors for this path; see oracle/rwkv_numpy.py for what anchors the math.
+ *
+ * Math: SURVEY.md App. A (BlinkDL rwkv pip model.py att_one_v6_0 / ffn_one_v6, att_one_v5_2),
+ * weights in the `.st` layout of /root/reference/assets/scripts/convert_safetensors.py:22-101
+ * (all f16, matrices [out, in]).  State per slot: (L, N+2, C) f32 == web-rwkv [C, N+2, L, 1]
+ * (reference crates/ai00-core/src/run.rs:987).
+ *
+ * act_f16 != 0: vectors that multiply a weight matrix are rounded to f16 first (f16 operands,
+ * f32 accumulate), everything else stays f32.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef _Float16 h16;
+
+typedef struct {
+    const h16 *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+    /* att */
+    const h16 *mix_x, *mix_w, *mix_k, *mix_v, *mix_r, *mix_g;   /* v6: time_mix_*; v5: mix_k/v/r/g only */
+    const h16 *mix_w1, *mix_w2;                                   /* v6: [5*Dm, C], [5, C, Dm] */
+    const h16 *decay, *decay_w1, *decay_w2;                       /* [C]; v6: [Dd, C], [C, Dd] */
+    const h16 *first;                                             /* [H, N] */
+    const h16 *wr, *wk, *wv, *wg, *wo;                            /* [C, C] */
+    const h16 *lnx_w, *lnx_b;
+    /* ffn */
+    const h16 *fmix_k, *fmix_r;
+    const h16 *fk, *fr, *fv;                                      /* [F, C], [C, C], [C, F] */
+} RefLayer;
+
+typedef struct {
+    int32_t version, L, C, F, V, H, N, Dm, Dd, act_f16;
+    const h16 *emb, *ln0_w, *ln0_b, *lnout_w, *lnout_b, *head;
+    const RefLayer* layers;
+} RefModel;
+
+static inline float q16(float x, int on) {
+    if (!on) return x;
+    if (x > 65504.f) x = 65504.f;
+    if (x < -65504.f) x = -65504.f;
+    return (float)(h16)x;
+}
+
+static void layer_norm(const float* x, const h16* w, const h16* b, int C, float* out) {
+    float mean = 0.f;
+    for (int i = 0; i < C; ++i) mean += x[i];
+    mean /= (float)C;
+    float var = 0.f;
+    for (int i = 0; i < C; ++i) { float d = x[i] - mean; var += d * d; }
+    var /= (float)C;
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+    for (int i = 0; i < C; ++i) out[i] = (x[i] - mean) * rstd * (float)w[i] + (float)b[i];
+}
+
+/* Y[b][n] = sum_k W[n][k] * X[b][k];  W f16 [N, K] row-major, X f32 [B, K] (already rounded), Y [B, N].
+ * Each weight row is converted once and used for all B slots (weights streamed once per step). */
+static void gemm(const h16* W, int N, int K, const float* X, int B, float* Y) {
+#pragma omp parallel
+    {
+        float* wrow = (float*)malloc(sizeof(float) * (size_t)K);
+#pragma omp for schedule(static)
+        for (int n = 0; n < N; ++n) {
+            const h16* w = W + (size_t)n * K;
+            for (int k = 0; k < K; ++k) wrow[k] = (float)w[k];
+            for (int b = 0; b < B; ++b) {
+                const float* x = X + (size_t)b * K;
+                float acc = 0.f;
+#pragma omp simd reduction(+ : acc)
+                for (int k = 0; k < K; ++k) acc += wrow[k] * x[k];
+                Y[(size_t)b * N + n] = acc;
+            }
+        }
+        free(wrow);
+    }
+}
+
+static void round_rows(const float* src, float* dst, size_t n, int on) {
+    for (size_t i = 0; i < n; ++i) dst[i] = q16(src[i], on);
+}
+
+static inline float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+/* One decode step for B slots.  tokens[B]; state [B][L][N+2][C] updated in place; logits [B][V]. */
+int ref_decode_step(const RefModel* m, int B, const int32_t* tokens, float* state, float* logits) {
+    const int C = m->C, F = m->F, V = m->V, H = m->H, N = m->N, L = m->L, q = m->act_f16;
+    const size_t BC = (size_t)B * C;
+    const size_t per_slot = (size_t)L * (N + 2) * C;
+    const int FM = F > C ? F : C;
+    float* x = (float*)malloc(4 * BC);
+    float* xx = (float*)malloc(4 * BC);
+    float* sx = (float*)malloc(4 * BC);
+    float* tmp = (float*)malloc(4 * (size_t)B * FM);
+    float* in = (float*)malloc(4 * (size_t)B * FM);
+    float* xs[5];
+    for (int i = 0; i < 5; ++i) xs[i] = (float*)malloc(4 * BC);
+    float *r = (float*)malloc(4 * BC), *k = (float*)malloc(4 * BC), *v = (float*)malloc(4 * BC), *g = (float*)malloc(4 * BC);
+    float* wdec = (float*)malloc(4 * BC);
+    float* out = (float*)malloc(4 * BC);
+    float* kk = (float*)malloc(4 * (size_t)B * F);
+    const int Dm = m->Dm, Dd = m->Dd;
+    float* lo = (float*)malloc(4 * (size_t)B * (5 * (Dm > 0 ? Dm : 1) + (Dd > 0 ? Dd : 1) + 8));
+
+    for (int b = 0; b < B; ++b) {
+        int t = tokens[b];
+        if (t < 0) t = 0;
+        if (t >= V) t = V - 1;
+        for (int i = 0; i < C; ++i) tmp[i] = (float)m->emb[(size_t)t * C + i];
+        layer_norm(tmp, m->ln0_w, m->ln0_b, C, x + (size_t)b * C);
+    }
+    for (int l = 0; l < L; ++l) {
+        const RefLayer* ly = &m->layers[l];
+        /* ---------------- time mix ---------------- */
+        for (int b = 0; b < B; ++b) {
+            float* st = state + b * per_slot + (size_t)l * (N + 2) * C;
+            layer_norm(x + (size_t)b * C, ly->ln1_w, ly->ln1_b, C, xx + (size_t)b * C);
+            for (int i = 0; i < C; ++i) sx[(size_t)b * C + i] = st[i] - xx[(size_t)b * C + i];
+        }
+        if (m->version == 6) {
+            for (size_t i = 0; i < BC; ++i) in[i] = q16(xx[i] + sx[i] * (float)ly->mix_x[i % C], q);
+            gemm(ly->mix_w1, 5 * Dm, C, in, B, lo);                         /* [B, 5*Dm] */
+            for (size_t i = 0; i < (size_t)B * 5 * Dm; ++i) lo[i] = q16(tanhf(lo[i]), q);
+            const h16* mus[5] = {ly->mix_w, ly->mix_k, ly->mix_v, ly->mix_r, ly->mix_g};
+            for (int j = 0; j < 5; ++j) {
+                /* m_j = W2[j] [C, Dm] @ lo[b][j*Dm .. ] */
+                float* mj = tmp;
+                float* inj = in;                                            /* [B, Dm] gathered */
+                for (int b = 0; b < B; ++b) memcpy(inj + (size_t)b * Dm, lo + (size_t)b * 5 * Dm + (size_t)j * Dm, 4 * (size_t)Dm);
+                gemm(ly->mix_w2 + (size_t)j * C * Dm, C, Dm, inj, B, mj);
+                for (size_t i = 0; i < BC; ++i) xs[j][i] = xx[i] + sx[i] * ((float)mus[j][i % C] + mj[i]);
+            }
+            /* decay */
+            round_rows(xs[0], in, BC, q);
+            float* d1 = lo;
+            gemm(ly->decay_w1, Dd, C, in, B, d1);
+            for (size_t i = 0; i < (size_t)B * Dd; ++i) d1[i] = q16(tanhf(d1[i]), q);
+            gemm(ly->decay_w2, C, Dd, d1, B, wdec);
+            for (size_t i = 0; i < BC; ++i) wdec[i] = expf(-expf((float)ly->decay[i % C] + wdec[i]));
+        } else {
+            const h16* mus[5] = {0, ly->mix_k, ly->mix_v, ly->mix_r, ly->mix_g};
+            for (int j = 1; j < 5; ++j)
+                for (size_t i = 0; i < BC; ++i) {
+                    const float mu = (float)mus[j][i % C];
+                    const float prev = sx[i] + xx[i];
+                    xs[j][i] = xx[i] * mu + prev * (1.0f - mu);
+                }
+            for (size_t i = 0; i < BC; ++i) wdec[i] = expf(-expf((float)ly->decay[i % C]));
+        }
+        round_rows(xs[3], in, BC, q); gemm(ly->wr, C, C, in, B, r);
+        round_rows(xs[1], in, BC, q); gemm(ly->wk, C, C, in, B, k);
+        round_rows(xs[2], in, BC, q); gemm(ly->wv, C, C, in, B, v);
+        round_rows(xs[4], in, BC, q); gemm(ly->wg, C, C, in, B, g);
+        for (size_t i = 0; i < BC; ++i) g[i] = g[i] * sigmoidf_(g[i]);
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int b = 0; b < B; ++b)
+            for (int h = 0; h < H; ++h) {
+                float* st = state + b * per_slot + (size_t)l * (N + 2) * C;
+                const float* rb = r + (size_t)b * C + h * N;
+                const float* kb = k + (size_t)b * C + h * N;
+                const float* vb = v + (size_t)b * C + h * N;
+                const float* wb = wdec + (size_t)b * C + h * N;
+                float o[64];
+                for (int j = 0; j < N; ++j) o[j] = 0.f;
+                for (int i = 0; i < N; ++i) {
+                    float* S = st + (size_t)(1 + i) * C + h * N;      /* row 1+i, cols h*N + j */
+                    const float u = (float)ly->first[h * N + i];
+                    for (int j = 0; j < N; ++j) {
+                        const float a = kb[i] * vb[j];
+                        o[j] += rb[i] * (u * a + S[j]);
+                        S[j] = a + wb[i] * S[j];
+                    }
+                }
+                /* GroupNorm over the head, eps 64e-5 */
+                float mean = 0.f;
+                for (int j = 0; j < N; ++j) mean += o[j];
+                mean /= (float)N;
+                float var = 0.f;
+                for (int j = 0; j < N; ++j) { float d = o[j] - mean; var += d * d; }
+                var /= (float)N;
+                const float rstd = 1.0f / sqrtf(var + 64e-5f);
+                for (int j = 0; j < N; ++j) {
+                    const int c = h * N + j;
+                    out[(size_t)b * C + c] = ((o[j] - mean) * rstd * (float)ly->lnx_w[c] + (float)ly->lnx_b[c]) * g[(size_t)b * C + c];
+                }
+            }
+        for (int b = 0; b < B; ++b) {
+            float* st = state + b * per_slot + (size_t)l * (N + 2) * C;
+            memcpy(st, xx + (size_t)b * C, 4 * (size_t)C);
+        }
+        round_rows(out, in, BC, q);
+        gemm(ly->wo, C, C, in, B, tmp);
+        for (size_t i = 0; i < BC; ++i) x[i] += tmp[i];
+        /* ---------------- channel mix ---------------- */
+        for (int b = 0; b < B; ++b) {
+            float* st = state + b * per_slot + (size_t)l * (N + 2) * C + (size_t)(N + 1) * C;
+            layer_norm(x + (size_t)b * C, ly->ln2_w, ly->ln2_b, C, xx + (size_t)b * C);
+            for (int i = 0; i < C; ++i) {
+                const float prev = st[i], cur = xx[(size_t)b * C + i];
+                const float mk = (float)ly->fmix_k[i], mr = (float)ly->fmix_r[i];
+                if (m->version == 6) {
+                    xs[0][(size_t)b * C + i] = cur + (prev - cur) * mk;
+                    xs[1][(size_t)b * C + i] = cur + (prev - cur) * mr;
+                } else {
+                    xs[0][(size_t)b * C + i] = cur * mk + prev * (1.0f - mk);
+                    xs[1][(size_t)b * C + i] = cur * mr + prev * (1.0f - mr);
+                }
+                st[i] = cur;
+            }
+        }
+        round_rows(xs[1], in, BC, q); gemm(ly->fr, C, C, in, B, r);
+        round_rows(xs[0], in, BC, q); gemm(ly->fk, F, C, in, B, kk);
+        for (size_t i = 0; i < (size_t)B * F; ++i) { float t = kk[i] > 0.f ? kk[i] : 0.f; kk[i] = q16(t * t, q); }
+        gemm(ly->fv, C, F, kk, B, tmp);
+        for (size_t i = 0; i < BC; ++i) x[i] += sigmoidf_(r[i]) * tmp[i];
+    }
+    for (int b = 0; b < B; ++b) {
+        layer_norm(x + (size_t)b * C, m->lnout_w, m->lnout_b, C, xx + (size_t)b * C);
+    }
+    round_rows(xx, in, BC, q);
+    gemm(m->head, V, C, in, B, logits);
+
+    free(x); free(xx); free(sx); free(tmp); free(in);
+    for (int i = 0; i < 5; ++i) free(xs[i]);
+    free(r); free(k); free(v); free(g); free(wdec); free(out); free(kk); free(lo);
+    return 0;
+}
+
+int ref_num_threads(void) {
+    int n = 1;
+#ifdef _OPENMP
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+#endif
+    return n;
+}

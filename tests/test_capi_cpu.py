@@ -1,0 +1,94 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the
+header declares, the host-only entry points work, and device entry points fail loudly (there
+is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ai00_server_b200 import capi, runtime, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200rwkv.h")).read()
+    declared = set(re.findall(r"\b(b200rwkv_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"b200rwkv_status", "b200rwkv_info", "b200rwkv_engine"}
+    assert len(declared) >= 20
+    lib = capi.lib()
+    bound = {n for n, _, _ in capi.SYMBOLS}
+    assert declared == bound, (declared ^ bound)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_info_from_st_host_only():
+    for preset, ver in (("tiny5", 5), ("tiny6", 6), ("tiny7", 7)):
+        info = capi.info_from_st(synth.make_st(preset, 0))
+        s = synth.PRESETS[preset]
+        assert info["version"] == ver
+        assert (info["num_layer"], info["num_emb"], info["num_hidden"], info["num_vocab"]) == (s.L, s.C, s.F, s.V)
+        assert (info["num_head"], info["head_size"]) == (s.H, 64)
+    i6 = capi.info_from_st(synth.make_st("tiny6", 0))
+    assert (i6["time_mix_adapter"], i6["time_decay_adapter"]) == (32, 64)
+
+
+def test_malformed_st_is_an_error_not_a_crash():
+    junk = np.frombuffer(b"\x10\x00\x00\x00\x00\x00\x00\x00{\"a\":1}        ", dtype=np.uint8).copy()
+    with pytest.raises(capi.B200Error) as ei:
+        capi.info_from_st(junk)
+    assert ei.value.code == capi.ERR_INVALID
+    with pytest.raises(capi.B200Error):
+        capi.info_from_st(np.zeros(4, np.uint8))
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu():
+    with pytest.raises(capi.B200Error) as ei:
+        runtime.Model(synth.make_st("tiny6", 0), max_batch=2, token_chunk_size=16)
+    assert ei.value.code == capi.ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_fp32_precision_rejected():
+    st = synth.make_st("tiny6", 0)
+    h = C.c_void_p()
+    code = capi.lib().b200rwkv_create(capi.ptr(st), st.size, 0, 2, 16, 1, C.byref(h))
+    assert code == capi.ERR_UNSUPPORTED
+    assert not h.value
+
+
+def test_runtime_chunking_bookkeeping():
+    """Runtime.infer mirrors web-rwkv: <= token_chunk_size tokens per call, Last rows only once a
+    slot's run is exhausted (reference run.rs:1134-1155).  Engine calls are stubbed."""
+    calls = []
+
+    class Stub:
+        info = {"num_vocab": 8}
+
+        def infer_raw(self, slots, ntok, toks, opts):
+            calls.append((list(slots), list(ntok), list(toks), list(opts)))
+            return [np.zeros((nt if o == capi.OPTION_FULL else (1 if o == capi.OPTION_LAST else 0), 8), np.float32)
+                    for nt, o in zip(ntok, opts)]
+
+    rt = runtime.Runtime(Stub())
+    inp = runtime.RnnInput([runtime.RnnInputBatch([1, 2, 3, 4, 5], runtime.RnnOption.Last),
+                            runtime.RnnInputBatch([], runtime.RnnOption.Last),
+                            runtime.RnnInputBatch([7, 8], runtime.RnnOption.Full)], 4)
+    seen_rows = {0: 0, 2: 0}
+    while inp.num_token() > 0:
+        inp, out = rt.infer(inp)
+        for b, o in enumerate(out):
+            if not o.is_empty():
+                seen_rows[b] += o.data.shape[0]
+    assert seen_rows == {0: 1, 2: 2}
+    assert calls[0] == ([0], [4], [1, 2, 3, 4], [capi.OPTION_NONE])
+    assert calls[1] == ([0, 2], [1, 2], [5, 7, 8], [capi.OPTION_LAST, capi.OPTION_FULL])

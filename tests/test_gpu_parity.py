@@ -1,0 +1,222 @@
+"""GPU parity tests: the CUDA engine, called through the C ABI (ai00_server_b200.runtime is a thin
+ctypes mirror of the reference's Runtime/State interface), against the CPU oracle on the same
+seeded synthetic `.st` weights and against the committed golden fixtures.
+
+Tolerance (BASELINE.json north_star): logits within 1e-3 relative, argmax token ids exact.
+"relative" is measured against the logits range: max|d| / max|logits|.  The engine and the
+oracle's "f16" contract round the same operands to f16, so the observed error is ~1e-5; the
+"f32" contract (no activation rounding at all) must also stay inside 1e-3.
+"""
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+
+from ai00_server_b200 import capi, runtime, synth
+from oracle import rwkv_numpy as O
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3
+
+
+def rel_err(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def models():
+    cache = {}
+
+    def get(preset, seed=0, max_batch=4, chunk=32, **over):
+        key = (preset, seed, max_batch, chunk, tuple(sorted(over.items())))
+        if key not in cache:
+            shp = synth.PRESETS[preset] if not over else dataclasses.replace(synth.PRESETS[preset], **over)
+            st = synth.make_st(shp, seed)
+            cache[key] = (runtime.Model(st, max_batch=max_batch, token_chunk_size=chunk), O.Oracle(O.parse_st(st), "f16"), st)
+        return cache[key]
+
+    yield get
+    for m, _, _ in cache.values():
+        m.close()
+
+
+def feed(model, slot, tokens, full=False):
+    rows = model.infer_raw([slot], [len(tokens)], list(tokens), [capi.OPTION_FULL if full else capi.OPTION_LAST])
+    return rows[0].copy()
+
+
+@pytest.mark.parametrize("preset", ["tiny6", "tiny5", "tiny7", "small6"])
+def test_logits_match_oracle(models, preset):
+    m, orc, st = models(preset)
+    toks = [1, 5, 9, 33, 2, 7, 300, 41, 41, 8, 0, 17]
+    m.state.load(m.state.init(), 0)
+    got = feed(m, 0, toks, full=True)
+    want, want_state = orc.run(toks, orc.state_init(), full=True)
+    assert got.shape == want.shape
+    assert rel_err(got, want) <= REL_TOL
+    assert (got.argmax(1) == want.argmax(1)).all()
+    # the f32 activation contract is the other face of the tolerance budget
+    want32, _ = O.Oracle(O.parse_st(st), "f32").run(toks, orc.state_init(), full=True)
+    assert rel_err(got, want32) <= REL_TOL
+    assert (got.argmax(1) == want32.argmax(1)).all()
+    # state after the run, through State::back, in the web-rwkv layout
+    back = m.state.back(0)
+    assert rel_err(back, want_state) <= REL_TOL
+
+
+@pytest.mark.parametrize("preset", ["tiny5", "tiny6", "tiny7"])
+def test_logits_match_committed_goldens(models, preset, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"model_{preset}.npz"))
+    m, _, _ = models(preset)
+    m.state.load(m.state.init(), 1)
+    got = feed(m, 1, list(g["tokens"]), full=True)
+    assert rel_err(got, g["logits_f16"]) <= REL_TOL
+    assert (got.argmax(1) == g["logits_f16"].argmax(1)).all()
+    assert rel_err(m.state.back(1), g["state_f16"]) <= REL_TOL
+
+
+@pytest.mark.parametrize("preset", ["tiny6", "tiny7"])
+def test_decode_matches_prefill_and_chunking(models, preset):
+    """Token-by-token decode == one prefill call == ragged chunks (A4: results must not depend on
+    how web-rwkv's token_chunk_size cuts the input)."""
+    m, orc, _ = models(preset)
+    rng = np.random.default_rng(7)
+    toks = rng.integers(1, 500, size=45).tolist()
+    zero = m.state.init()
+    m.state.load(zero, 0)
+    a = feed(m, 0, toks)                       # 45 tokens: spans two internal steps (chunk 32)
+    m.state.load(zero, 1)
+    for t in toks[:-1]:
+        feed(m, 1, [t])
+    b = feed(m, 1, toks[-1:])
+    m.state.load(zero, 2)
+    feed(m, 2, toks[:7]); feed(m, 2, toks[7:30])
+    c = feed(m, 2, toks[30:])
+    want, _ = orc.run(toks, orc.state_init())
+    for got in (a, b, c):
+        assert rel_err(got, want) <= REL_TOL
+        assert got.argmax() == want.argmax()
+    assert rel_err(a, b) <= 1e-4 and rel_err(a, c) <= 1e-4
+    assert rel_err(m.state.back(0), m.state.back(1)) <= 1e-4
+
+
+def test_batching_invariance_and_ragged_batch(models):
+    """Logits of slot i are independent of what the other slots do."""
+    m, orc, _ = models("tiny6")
+    rng = np.random.default_rng(11)
+    runs = [rng.integers(1, 500, size=n).tolist() for n in (1, 6, 3, 9)]
+    zero = m.state.init()
+    for s in range(4):
+        m.state.load(zero, s)
+    rows = m.infer_raw([0, 1, 2, 3], [len(r) for r in runs], [t for r in runs for t in r],
+                       [capi.OPTION_LAST, capi.OPTION_FULL, capi.OPTION_LAST, capi.OPTION_LAST])
+    assert [r.shape[0] for r in rows] == [1, 6, 1, 1]
+    for s, r in enumerate(runs):
+        want, _ = orc.run(r, orc.state_init(), full=(s == 1))
+        assert rel_err(rows[s], want) <= REL_TOL
+        assert (rows[s].argmax(1) == want.argmax(1)).all()
+    # same runs alone: bit-identical (deterministic reductions, no atomics)
+    m.state.load(zero, 2)
+    alone = feed(m, 2, runs[2])
+    assert np.array_equal(alone, rows[2])
+
+
+def test_runtime_infer_loop_like_the_reference_shim(models):
+    """Drive Runtime.infer exactly as ai00-core's infer() does (run.rs:1120-1155)."""
+    m, orc, _ = models("tiny6", chunk=8, max_batch=4)
+    zero = m.state.init()
+    for s in range(4):
+        m.state.load(zero, s)
+    prompts = {0: [5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15], 2: [3, 4]}
+    batches = [runtime.RnnInputBatch(prompts.get(b, []), runtime.RnnOption.Last) for b in range(4)]
+    inp = runtime.RnnInput(batches, 8)
+    got = {}
+    calls = 0
+    while inp.num_token() > 0:
+        inp, out = m.runtime.infer(inp)
+        calls += 1
+        for b, o in enumerate(out):
+            if not o.is_empty():
+                got[b] = o.data.copy()
+    assert calls == 2 and set(got) == {0, 2}
+    for b, p in prompts.items():
+        want, _ = orc.run(p, orc.state_init())
+        assert rel_err(got[b], want) <= REL_TOL and got[b].argmax() == want.argmax()
+
+
+def test_state_roundtrip_and_snapshots(models):
+    m, orc, _ = models("tiny6")
+    rng = np.random.default_rng(5)
+    st = rng.standard_normal(m.state.init().shape).astype(np.float32)
+    m.state.load(st, 3)
+    assert np.array_equal(m.state.back(3), st)            # load o back = id (A2)
+    # continue from an arbitrary state == oracle from the same state
+    got = feed(m, 3, [9, 8, 7])
+    want, want_st = orc.run([9, 8, 7], st)
+    assert rel_err(got, want) <= REL_TOL
+    assert rel_err(m.state.back(3), want_st) <= REL_TOL
+    # read / write: device-side snapshot restores the slot (reference run.rs:937, 979)
+    snap = m.state.read(3)
+    before = m.state.back(3)
+    feed(m, 3, [1, 2, 3, 4])
+    assert not np.array_equal(m.state.back(3), before)
+    m.state.write(snap, 3)
+    assert np.array_equal(m.state.back(3), before)
+    m.state.write(snap, 0)                                  # snapshots move between slots
+    assert np.array_equal(m.state.back(0), before)
+    snap.free()
+    with pytest.raises(capi.B200Error) as ei:
+        m.state.write(runtime.TensorGpu(m, 424242), 0)
+    assert ei.value.code == capi.ERR_STATE
+
+
+def test_state_init_with_time_state(models):
+    m, orc, _ = models("tiny6", time_state=True)
+    init = m.state.init()
+    assert np.array_equal(init, orc.state_init())
+    assert np.abs(init[:, 1:65]).max() > 0
+    m.state.load(init, 0)
+    got = feed(m, 0, [4, 5, 6])
+    want, _ = orc.run([4, 5, 6], orc.state_init())
+    assert rel_err(got, want) <= REL_TOL
+
+
+def test_softmax_matches_oracle(models):
+    m, _, _ = models("tiny6")
+    x = np.random.default_rng(3).standard_normal((5, m.info["num_vocab"])).astype(np.float32) * 4
+    got = np.stack(m.softmax([r for r in x]))
+    want = O.softmax_rows(x)
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(got.sum(1), 1.0, atol=1e-5)
+
+
+def test_error_behaviour(models):
+    m, _, _ = models("tiny6")
+    with pytest.raises(capi.B200Error) as ei:
+        m.infer_raw([99], [1], [1], [capi.OPTION_LAST])
+    assert ei.value.code == capi.ERR_STATE
+    with pytest.raises(capi.B200Error) as ei:
+        m.infer_raw([0, 0], [1, 1], [1, 2], [capi.OPTION_LAST, capi.OPTION_LAST])
+    assert ei.value.code == capi.ERR_INVALID
+    rows = m.infer_raw([0], [0], [], [capi.OPTION_LAST])     # empty run: no output (RnnOutputBatch empty)
+    assert rows[0].shape[0] == 0
+
+
+def test_wkv_kernels_reproduce_fla_fixtures(models, golden_dir):
+    """Independent pin: drive the engine's WKV state through State::load/back around one decode
+    step and compare the recurrence with fla's naive result is not possible in isolation through
+    the C ABI, so this checks the property the fixture pins at model level: the state rows the
+    engine returns equal the oracle recurrence, which itself reproduces the fla fixture
+    (tests/test_oracle.py)."""
+    g = np.load(os.path.join(golden_dir, "wkv6_fla.npz"))
+    m, orc, _ = models("tiny6")
+    st = m.state.init()
+    H = m.info["num_head"]
+    S0 = np.tile(g["S0"], (2, 1, 1))[:H]                       # [H, i, j]
+    st[0, 1:65] = S0.transpose(1, 0, 2).reshape(64, H * 64)
+    m.state.load(st, 0)
+    feed(m, 0, [12])
+    _, want = orc.run([12], st)
+    assert rel_err(m.state.back(0)[0, 1:65], want[0, 1:65]) <= 1e-5
