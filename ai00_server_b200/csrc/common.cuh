@@ -30,12 +30,14 @@ struct MetaView {
 };
 
 // ---------------------------------------------------------------------------------------
-// "A16" activation layout: the f16 operand of every projection, stored so that the
-// k-range a GEMM stage needs is one contiguous 2 KB run per 16-token tile:
-//   [m_tile][k32 block][16 rows][32 halves]
+// "A16" activation layout: the f16 operand of every projection, stored as the UMMA canonical
+// K-major / no-swizzle layout of a 16-token tile so that (a) the k-range a GEMM stage needs is one
+// contiguous 2 KB run (one bulk TMA copy) and (b) tcgen05.mma reads it from shared memory as is:
+//   [m_tile][k8 chunk][16 token rows][8 halves]      (8 rows x 16 B = one 128-byte core matrix)
+// `kq_per_tile` = padded K / 32 (k32 blocks per tile), so K / 8 = 4 * kq_per_tile chunks.
 // ---------------------------------------------------------------------------------------
 __host__ __device__ inline size_t a16_index(int m, int k, int kq_per_tile) {
-    return (((size_t)(m >> 4) * kq_per_tile + (k >> 5)) * 16 + (m & 15)) * 32 + (k & 31);
+    return (((size_t)(m >> 4) * (4 * kq_per_tile) + (k >> 3)) * 16 + (m & 15)) * 8 + (k & 7);
 }
 
 __device__ __forceinline__ __half f2h_sat(float v) {
@@ -99,6 +101,39 @@ __device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uin
         "l"(src), "r"(bytes), "r"(bar), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned atom_add_acq_rel_gpu(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -115,6 +150,57 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ---------------------------------------------------------------------------------------
+// tcgen05 (5th-gen tensor core) wrappers: TMEM allocation, single-thread MMA issue, commit to an
+// mbarrier, TMEM -> register loads.  SASS: UTCHMMA / UTCBAR / LDTM.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// whole warp; writes the TMEM base address to shared memory at `smem_dst`
+__device__ __forceinline__ void tc_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 B
+// contiguous); lbo = byte distance between the two 16-byte k chunks of one k16 step, sbo = byte
+// distance between 8-row groups.  Bits [46,48) = 1: Blackwell descriptor version.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16: f16 x f16 -> f32, both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns -> 16 registers per thread (lane i of the warp = TMEM lane base+i)
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // Programmatic dependent launch: everything before this call may overlap the tail of the
@@ -135,18 +221,38 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-// block-wide sum; `red` is >= 32 floats of shared memory; result broadcast to all threads
+// CTA-wide sync domain: stand-alone kernels sync the whole CTA; inside the persistent whole-step
+// kernel (mega.cuh) only the 256 consumer threads take part (the producer warp runs free).
+constexpr int CONSUMER_THREADS = 256;
+template <bool MEGA>
+__device__ __forceinline__ void cta_sync() {
+    if (MEGA) named_bar_sync(1, CONSUMER_THREADS);
+    else __syncthreads();
+}
+// block-wide sum over 256 threads; `red` is >= 8 floats of shared memory; result broadcast
+template <bool MEGA>
 __device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    cta_sync<MEGA>();   // protect `red` from the previous use
+    if (lane == 0) red[warp] = v;
+    cta_sync<MEGA>();
+    float t = (lane < CONSUMER_THREADS / 32) ? red[lane] : 0.f;
+    t = warp_sum(t);
+    return t;
+}
+// generic versions for kernels with other block sizes (softmax)
+__device__ __forceinline__ float block_sum_any(float v, float* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     v = warp_sum(v);
-    __syncthreads();   // protect `red` from the previous use
+    __syncthreads();
     if (lane == 0) red[warp] = v;
     __syncthreads();
     float t = (lane < nw) ? red[lane] : 0.f;
     t = warp_sum(t);
     return t;
 }
-__device__ __forceinline__ float block_max(float v, float* red) {
+__device__ __forceinline__ float block_max_any(float v, float* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     v = warp_max(v);
     __syncthreads();

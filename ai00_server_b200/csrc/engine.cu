@@ -16,8 +16,10 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "mega.cuh"
 #include "misc.cuh"
 #include "mix.cuh"
+#include "streamtest.cuh"
 #include "wkv.cuh"
 
 namespace b200 {
@@ -269,6 +271,7 @@ struct A16Buf {
 struct Layer {
     LnMixParams ln1, ln2;
     std::vector<GemmLaunch> pre;    // launches between LN1 and WKV
+    int wd2_index = -1;             // v6: index in `pre` of the decay-LoRA stage-2 launch (folded into the WKV phase by the megakernel)
     WkvParams wkv;
     GemmLaunch o;
     std::vector<GemmLaunch> ffn;    // launches after LN2
@@ -291,6 +294,10 @@ struct b200rwkv_engine {
     int S = 0, chunk = 0, maxT = 64;
     int L = 0, C = 0, F = 0, V = 0, H = 0, N = 64, Cl = 0, Hl = 0, Fl = 0, Vl = 0;
     bool use_graph = true, use_pdl = true;
+    bool use_mega = true, mega_ok = false;
+    MegaParams mega;
+    std::vector<int> mega_phase_types;
+    int skip_mask = 0;   // timing attribution only (B200RWKV_SKIP): 1 LN, 2 small GEMMs, 4 WKV, 8 big GEMMs, 16 head
     cudaStream_t stream = nullptr, sm_stream = nullptr;
     std::vector<void*> allocs;
     size_t weight_bytes_total = 0;
@@ -343,7 +350,8 @@ struct b200rwkv_engine {
     float* vec_f32(const StFile& st, const std::string& name, size_t off, size_t count, float scale = 1.f, float bias = 0.f);
     A16Buf a16_alloc(int K, int nmat = 1);
     GemmLaunch make_launch(std::vector<SegDesc>& segs);
-    void finalize_ws();
+    void build_mega(const StFile& st);
+    void launch_mega(cudaStream_t s);
 
     template <typename P>
     void launch_k(void (*kern)(P), dim3 grid, dim3 block, size_t smem, const P& params, int cls, cudaStream_t s, Profiler* prof);
@@ -462,6 +470,8 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs) {
     g.p.max_contrib = cdiv(kbmax, per_cta) + 1;
     g.p.counters = (unsigned*)dalloc((size_t)tile * 4, true);
     g.p.nrows = d_meta;   // T by default
+    g.p.w_lbo = GEMM_W_LBO; g.p.w_sbo = GEMM_W_SBO; g.p.a_lbo = GEMM_A_LBO; g.p.a_sbo = GEMM_A_SBO;
+    if (getenv("B200RWKV_UMMA_SWAP")) { std::swap(g.p.w_lbo, g.p.w_sbo); std::swap(g.p.a_lbo, g.p.a_sbo); }   // bring-up aid
     gemm_ws_floats = std::max(gemm_ws_floats, (size_t)tile * g.p.max_contrib * (size_t)maxT * GEMM_BN);
     weight_bytes_total += g.weight_bytes;
     return g;
@@ -687,6 +697,7 @@ void b200rwkv_engine::build(const StFile& st) {
                 std::vector<SegDesc> sv;
                 sv.push_back(f32_seg(st.get(a + "time_decay_w2"), c0, Cl, 0, Dd, a_lora[1].p, f_w, Cl, ACT_EXPNEGEXP,
                                      vec_f32(st, a + "time_decay", c0, Cl)));
+                ly.wd2_index = (int)ly.pre.size();
                 ly.pre.push_back(make_launch(sv));
             }
             wk.w = f_w;
@@ -833,9 +844,111 @@ void b200rwkv_engine::build(const StFile& st) {
     }
     head.p.ws = gemm_ws;
 
+    build_mega(st);
     CK(cudaDeviceSynchronize());
     CK(cudaFree(d_tmp));
     d_tmp = nullptr;
+}
+
+// -----------------------------------------------------------------------------------------
+// whole-step persistent kernel: device-side phase program over the same parameter blocks
+// -----------------------------------------------------------------------------------------
+void b200rwkv_engine::build_mega(const StFile& st) {
+    mega_ok = false;
+    const int ver = info.version;
+    const int Dd = info.time_decay_adapter;
+    if (!use_mega) return;
+    if (ver == 6 && (Dd > MEGA_MAX_DD || Dd % 8 != 0)) return;
+    if (C > MEGA_MAX_C) return;
+    std::vector<Phase> phases;
+    std::vector<LnMixParams> lns;
+    std::vector<GemmLaunchDev> gemms;
+    std::vector<WkvParams> wkvs;
+    auto add_gemm = [&](const GemmLaunch& g) {
+        GemmLaunchDev d;
+        memset(&d, 0, sizeof(d));
+        d.p = g.p;
+        d.ncta = g.grid;
+        phases.push_back({PH_GEMM, (int)gemms.size()});
+        gemms.push_back(d);
+    };
+    phases.push_back({PH_EMBED, 0});
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = layers[l];
+        phases.push_back({PH_LN, (int)lns.size()});
+        lns.push_back(ly.ln1);
+        for (int i = 0; i < (int)ly.pre.size(); ++i)
+            if (i != ly.wd2_index) add_gemm(ly.pre[i]);
+        WkvParams w = ly.wkv;
+        if (ver == 6) {
+            // k-major copy of this rank's time_decay_w2 rows, one contiguous [Dd][64] slice per head
+            const StTensor& t = st.get("blocks." + std::to_string(l) + ".att.time_decay_w2");
+            REQUIRE(t.shape.size() == 2 && t.shape[0] == C && t.shape[1] == Dd, B200RWKV_ERR_INVALID, "time_decay_w2 shape");
+            const __half* src = reinterpret_cast<const __half*>(t.data);
+            std::vector<__half> tmp((size_t)Hl * Dd * 64);
+            const int c0 = rank * Cl;
+            for (int h = 0; h < Hl; ++h)
+                for (int k = 0; k < Dd; ++k)
+                    for (int c = 0; c < 64; ++c) tmp[((size_t)h * Dd + k) * 64 + c] = src[(size_t)(c0 + h * 64 + c) * Dd + k];
+            __half* d = (__half*)dalloc(tmp.size() * 2, false);
+            CK(cudaMemcpy(d, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));
+            w.wd2t = d;
+            w.decay_bias = ly.pre[ly.wd2_index].p.seg[0].bias;
+            w.d1 = a_lora[1].p;
+            w.d1_kq = a_lora[1].kq;
+            w.Dd = Dd;
+        }
+        phases.push_back({PH_WKV, (int)wkvs.size()});
+        wkvs.push_back(w);
+        add_gemm(ly.o);
+        phases.push_back({PH_LN, (int)lns.size()});
+        lns.push_back(ly.ln2);
+        for (auto& g : ly.ffn) add_gemm(g);
+    }
+    phases.push_back({PH_LNOUT, 0});
+    add_gemm(head);
+
+    auto up = [&](const void* src, size_t bytes) {
+        void* d = dalloc(bytes, false);
+        CK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+        return d;
+    };
+    memset(&mega, 0, sizeof(mega));
+    mega.phases = (const Phase*)up(phases.data(), phases.size() * sizeof(Phase));
+    mega.nphase = (int)phases.size();
+    mega.version = ver;
+    mega.embed = (const EmbedParams*)up(&embed, sizeof(embed));
+    mega.ln = (const LnMixParams*)up(lns.data(), lns.size() * sizeof(LnMixParams));
+    mega.gemm = (const GemmLaunchDev*)up(gemms.data(), gemms.size() * sizeof(GemmLaunchDev));
+    mega.wkv = (const WkvParams*)up(wkvs.data(), wkvs.size() * sizeof(WkvParams));
+    mega.lnout = (const LnOutParams*)up(&lnout, sizeof(lnout));
+    mega.gbar = (unsigned*)dalloc(16, true);
+    mega.meta = MetaView{d_meta, maxT, S};
+    if (getenv("B200RWKV_TRACE")) mega.trace = (unsigned long long*)dalloc((size_t)4 * phases.size() * 4 * 8, true);
+    mega_phase_types.clear();
+    for (auto& ph : phases) mega_phase_types.push_back(ph.type);
+    void (*kern)(MegaParams) = (ver == 6) ? mega_step_kernel<6> : (ver == 7 ? mega_step_kernel<7> : mega_step_kernel<5>);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM_BYTES));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, MEGA_THREADS, MEGA_SMEM_BYTES));
+    mega_ok = nb >= 1;
+}
+
+void b200rwkv_engine::launch_mega(cudaStream_t s) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(num_sms);
+    cfg.blockDim = dim3(MEGA_THREADS);
+    cfg.dynamicSmemBytes = MEGA_SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    void (*kern)(MegaParams) = (info.version == 6) ? mega_step_kernel<6> : (info.version == 7 ? mega_step_kernel<7> : mega_step_kernel<5>);
+    CK(cudaLaunchKernelEx(&cfg, kern, mega));
+    launches_last_step = 1;
 }
 
 // -----------------------------------------------------------------------------------------
@@ -844,39 +957,48 @@ void b200rwkv_engine::build(const StFile& st) {
 void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* prof) {
     launches_last_step = 0;
     const int rows = MT * 16;
-    launch_k(embed_ln0_kernel, dim3(rows), dim3(LN_THREADS), 0, embed, KC_LN, s, prof);
+    const int sk = skip_mask;
+    auto big = [](const GemmLaunch& g) { return g.weight_bytes >= (8u << 20); };
+    auto gemm = [&](const GemmLaunch& g) {
+        if (big(g) ? (sk & 8) : (sk & 2)) return;
+        launch_gemm(g, MT, s, prof);
+    };
+    if (!(sk & 1)) launch_k(embed_ln0_kernel, dim3(rows), dim3(LN_THREADS), (size_t)C * 4, embed, KC_LN, s, prof);
     const int wkv_slots = std::min(S, rows);
     for (int l = 0; l < L; ++l) {
         Layer& ly = layers[l];
-        launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, ly.ln1, KC_LN, s, prof);
-        for (auto& g : ly.pre) launch_gemm(g, MT, s, prof);
-        switch (info.version) {
+        if (!(sk & 1)) launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), (size_t)C * 4, ly.ln1, KC_LN, s, prof);
+        for (auto& g : ly.pre) gemm(g);
+        if (!(sk & 4)) switch (info.version) {
             case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof); break;
             case 6: launch_k(wkv_kernel<6>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof); break;
             default: launch_k(wkv_kernel<7>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof); break;
         }
-        launch_gemm(ly.o, MT, s, prof);
-        launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, ly.ln2, KC_LN, s, prof);
-        for (auto& g : ly.ffn) launch_gemm(g, MT, s, prof);
+        gemm(ly.o);
+        if (!(sk & 1)) launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), (size_t)C * 4, ly.ln2, KC_LN, s, prof);
+        for (auto& g : ly.ffn) gemm(g);
     }
-    launch_k(ln_out_kernel, dim3(rows), dim3(LN_THREADS), 0, lnout, KC_LN, s, prof);
-    if (MTR > 0) launch_gemm(head, MTR, s, prof);
+    if (!(sk & 1)) launch_k(ln_out_kernel, dim3(rows), dim3(LN_THREADS), (size_t)C * 4, lnout, KC_LN, s, prof);
+    if (MTR > 0 && !(sk & 16)) launch_gemm(head, MTR, s, prof);
 }
 
 static inline int mt_bucket(int rows) { return rows <= 16 ? 1 : (rows <= 32 ? 2 : 4); }
 
 void b200rwkv_engine::run_step(int MT, int MTR) {
+    const bool mega_step = mega_ok && MT == 1 && MTR <= 1;
     if (!use_graph) {
-        enqueue_step(stream, MT, MTR, nullptr);
+        if (mega_step) launch_mega(stream);
+        else enqueue_step(stream, MT, MTR, nullptr);
         return;
     }
-    const int key = MT * 8 + MTR;
+    const int key = mega_step ? 0 : MT * 8 + MTR;
     auto it = graphs.find(key);
     if (it == graphs.end()) {
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         try {
-            enqueue_step(stream, MT, MTR, nullptr);
+            if (mega_step) launch_mega(stream);
+            else enqueue_step(stream, MT, MTR, nullptr);
         } catch (...) {
             cudaStreamEndCapture(stream, &g);
             if (g) cudaGraphDestroy(g);
@@ -920,6 +1042,27 @@ int b200rwkv_engine::fill_meta(int* m, const std::vector<int>& slots, const std:
         }
     }
     m[0] = T; m[1] = (int)slots.size(); m[2] = R;
+    // WKV unit shape for the whole-step kernel: slots per (head, group) unit that minimises the
+    // heaviest CTA's stage count under round-robin unit assignment
+    {
+        const int ns = (int)slots.size(), extra = (info.version == 6) ? 1 : 0;
+        int best = 1;
+        long best_cost = -1;
+        for (int gs = 1; gs <= MEGA_MAX_GROUP && ns > 0; ++gs) {
+            const int groups = cdiv(ns, gs), units = Hl * groups;
+            long cost = 0;
+            for (int c = 0; c < std::min(num_sms, units); ++c) {
+                long sum = 0;
+                for (int u = c; u < units; u += num_sms) {
+                    const int grp = u / Hl;
+                    sum += extra + std::min(gs, ns - grp * gs);
+                }
+                cost = std::max(cost, sum);
+            }
+            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = gs; }
+        }
+        m[3] = best;
+    }
     *R_out = R;
     return T;
 }
@@ -1047,6 +1190,8 @@ int32_t b200rwkv_create_tp(const uint8_t* st, size_t len, int32_t device, int32_
     e->S = max_batch; e->chunk = token_chunk_size;
     if (const char* v = getenv("B200RWKV_GRAPH")) e->use_graph = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_PDL")) e->use_pdl = atoi(v) != 0;
+    if (const char* v = getenv("B200RWKV_SKIP")) e->skip_mask = atoi(v);
+    if (const char* v = getenv("B200RWKV_MEGA")) e->use_mega = atoi(v) != 0;
     e->build(f);
     *out = e.release();
     API_END
@@ -1270,6 +1415,7 @@ int32_t b200rwkv_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_t* 
         long long per_step = 1;   // embed
         for (auto& ly : e->layers) per_step += 1 + (long long)ly.pre.size() + 1 + 1 + 1 + (long long)ly.ffn.size();
         per_step += 2;            // ln_out + head
+        if (e->mega_ok && MT == 1) per_step = 1;   // whole step = one persistent kernel
         *launches_out = per_step * steps;
     }
     CK(cudaEventDestroy(ea));
@@ -1368,6 +1514,108 @@ int32_t b200rwkv_debug_read(b200rwkv_engine* e, const char* name, float* out, si
         *errp_ = ex.what();
         return ex.code;
     }
+}
+
+// Test/profiling aid: per-phase globaltimer stamps of the last whole-step kernel (needs
+// B200RWKV_TRACE=1 at creation).  out: [4][nphase][2] u64; types: [nphase] phase types.
+int32_t b200rwkv_debug_trace(b200rwkv_engine* e, uint64_t* out, size_t cap, int32_t* types, int32_t* nphase) {
+    if (!e || !out || !types || !nphase) return B200RWKV_ERR_INVALID;
+    if (!e->mega_ok || !e->mega.trace) { e->err = "no trace (set B200RWKV_TRACE=1)"; return B200RWKV_ERR_INVALID; }
+    const size_t n = (size_t)4 * e->mega.nphase * 4;
+    if (cap < n) return B200RWKV_ERR_INVALID;
+    cudaSetDevice(e->dev);
+    cudaStreamSynchronize(e->stream);
+    if (cudaMemcpy(out, e->mega.trace, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return B200RWKV_ERR_CUDA;
+    for (int i = 0; i < e->mega.nphase; ++i) types[i] = e->mega_phase_types[i];
+    *nphase = e->mega.nphase;
+    return B200RWKV_OK;
+}
+
+// Profiling aid: time one projection launch class in isolation, round-robin over the layers so
+// every launch streams cold weights.  which: 0.. = index into the pre-WKV launches, 10 = output
+// projection, 20/21 = channel-mix launches, 30 = head.  Returns ms per launch and weight bytes.
+int32_t b200rwkv_debug_gemm_time(b200rwkv_engine* e, int32_t which, int32_t reps, float* ms_out, int64_t* bytes_out,
+                                 uint64_t* trace_out /* [L][8] stamps of CTA 0 for the last round, or null */) {
+    API_BEGIN(e)
+    REQUIRE(e && ms_out && bytes_out && reps >= 1, B200RWKV_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->dev));
+    auto pick = [&](int l) -> const GemmLaunch& {
+        Layer& ly = e->layers[l % e->L];
+        if (which == 30) return e->head;
+        if (which >= 20) { REQUIRE(which - 20 < (int)ly.ffn.size(), B200RWKV_ERR_INVALID, "no such launch"); return ly.ffn[which - 20]; }
+        if (which == 10) return ly.o;
+        REQUIRE(which < (int)ly.pre.size(), B200RWKV_ERR_INVALID, "no such launch");
+        return ly.pre[which];
+    };
+    // a valid 16-token meta so row masks are full
+    std::vector<int> m(e->meta_ints, 0);
+    m[0] = 16; m[1] = std::min(16, e->S); m[2] = 16;
+    CK(cudaMemcpy(e->d_meta, m.data(), e->meta_ints * 4, cudaMemcpyHostToDevice));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    const int n = reps * e->L;
+    unsigned long long* d_tr = nullptr;
+    if (trace_out) { CK(cudaMalloc(&d_tr, (size_t)e->L * 16 * 8)); CK(cudaMemset(d_tr, 0, (size_t)e->L * 16 * 8)); }
+    for (int i = 0; i < e->L; ++i) e->launch_gemm(pick(i), 1, e->stream, nullptr);
+    CK(cudaEventRecord(a, e->stream));
+    for (int i = 0; i < n; ++i) {
+        GemmLaunch g = pick(i);
+        if (d_tr && i >= n - e->L) g.p.trace = d_tr + (size_t)(i % e->L) * 16;
+        e->launch_gemm(g, 1, e->stream, nullptr);
+    }
+    CK(cudaEventRecord(b, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (d_tr) { CK(cudaMemcpy(trace_out, d_tr, (size_t)e->L * 16 * 8, cudaMemcpyDeviceToHost)); CK(cudaFree(d_tr)); }
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    *ms_out = ms / n;
+    *bytes_out = (int64_t)pick(0).weight_bytes;
+    API_END
+}
+
+// Streaming micro-benchmark (see streamtest.cuh).  kind 0: vector loads; kind 1: bulk-TMA ring.
+int32_t b200rwkv_debug_stream(int32_t device, int32_t kind, double gbytes, int32_t stage_bytes, int32_t nstage, int32_t use_hint,
+                              int32_t consumer, int32_t split, int32_t producers, int32_t reps, float* ms_out) {
+    int32_t extra = 0;
+    if (stage_bytes % 16384 != 0 && stage_bytes > 16384) { extra = stage_bytes % 16384; }
+    API_BEGIN((b200rwkv_engine*)nullptr)
+    REQUIRE(ms_out && reps >= 1, B200RWKV_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    const int G = prop.multiProcessorCount;
+    size_t per_cta = (size_t)(gbytes * 1e9 / G);
+    per_cta = per_cta / stage_bytes * stage_bytes;
+    const size_t total = per_cta * G;
+    uint8_t* buf = nullptr;
+    unsigned* sink = nullptr;
+    CK(cudaMalloc(&buf, total + 1024));
+    CK(cudaMalloc(&sink, 4));
+    CK(cudaMemset(buf, 0, total));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    StreamParams sp;
+    sp.src = buf; sp.bytes_per_cta = per_cta; sp.stage_bytes = stage_bytes; sp.nstage = nstage; sp.use_hint = use_hint;
+    sp.consumer = consumer; sp.split = split; sp.producers = producers; sp.extra = extra;
+    const size_t smem = (size_t)nstage * stage_bytes + 2 * nstage * 8 + 64;
+    if (kind == 1) CK(cudaFuncSetAttribute(stream_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int r = 0; r < reps + 1; ++r) {
+        if (r == 1) CK(cudaEventRecord(a));
+        if (kind == 0) stream_ldg_kernel<<<G * 8, 256>>>(reinterpret_cast<const uint4*>(buf), total / 16, sink);
+        else stream_ring_kernel<<<G, 128, smem>>>(sp);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(b));
+    CK(cudaDeviceSynchronize());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    *ms_out = ms / reps;
+    CK(cudaFree(buf));
+    CK(cudaFree(sink));
+    API_END
 }
 
 const char* b200rwkv_last_error(b200rwkv_engine* e) { return e ? e->err.c_str() : g_err.c_str(); }

@@ -6,21 +6,25 @@
 //
 // HBM-bound by construction (T <= 64 rows per pass, each weight byte is used once per step), so
 // the design is about keeping ~200 KB of weight bytes in flight per SM and never stalling the
-// stream:
+// stream.  At batch 16 the math is 16 FLOP per weight byte = ~100 TFLOP/s at HBM rate: measured
+// on B200 the legacy mma.sync path tops out near 140 TFLOP/s (HMMA.16816 issues once per 32
+// cycles per sub-partition; profiles/r01_gemm_mma_sync.md), so the tensor work is on tcgen05:
+//   * swap-AB: the WEIGHT tile is the 128-row M operand, the token tile is the N=16 operand, the
+//     f32 accumulator (128 lanes x 16 columns) lives in TMEM; one elected thread issues
+//     tcgen05.mma.cta_group::1.kind::f16, four k16 steps per 16 KB stage;
 //   * weights are re-tiled ONCE at load into 16 KB stage blocks (128 output rows x 64 k) already
-//     in the order the tensor-core B fragments are read, so a pipeline stage is ONE contiguous
-//     1-D bulk TMA copy (cp.async.bulk -> UBLKCP) and shared-memory reads are conflict-free
-//     128-bit loads with no ldmatrix/swizzle;
-//   * activations use the A16 layout (common.cuh) so a stage's X slice is one 2 KB bulk copy;
-//   * one producer lane drives a 9-12 stage mbarrier ring, 8 consumer warps issue
-//     mma.sync.m16n8k16 (tokens are the M=16 operand; the k index inside each 32-wide block is
-//     permuted identically for A and B so both are plain 16-byte row chunks);
+//     in the UMMA canonical K-major / no-swizzle shared-memory layout, so a pipeline stage is ONE
+//     contiguous 1-D bulk TMA copy (cp.async.bulk -> UBLKCP) that the tensor core reads in place;
+//     activations use the matching A16 layout (common.cuh): one 2 KB bulk copy per stage;
+//   * warp roles: one TMA producer lane drives a 9-12 stage mbarrier ring; one MMA lane consumes
+//     it (tcgen05.commit releases each slot when its MMAs retire); four epilogue warps drain the
+//     double-buffered TMEM accumulator with tcgen05.ld while the next tile's MMAs run;
 //   * work is split stream-K style: the launch's stage blocks (all segments, all tiles) form one
-//     linear sequence cut into gridDim.x equal contiguous ranges, so every SM streams the same
-//     number of bytes whatever the matrix shapes;
+//     linear sequence cut into equal contiguous ranges, so every SM streams the same number of
+//     bytes whatever the matrix shapes;
 //   * tiles cut across CTAs are reduced deterministically: each contributor writes its partial
 //     tile to an L2-resident workspace, bumps a per-tile counter, and the LAST arriver sums the
-//     partials in fixed slot order and runs the fused epilogue (no spinning, no float atomics).
+//     partials in fixed slot order and runs the fused epilogue (no spinning, no float atomics);
 //   * a launch carries up to 8 "segments" (independent matrices, own input, K and epilogue) so
 //     R/K/V/G + decay-LoRA, or the five ddlerp LoRAs, go out as ONE kernel.
 #pragma once
@@ -28,14 +32,20 @@
 
 namespace b200 {
 
-constexpr int GEMM_BN = 128;                 // output rows (weight rows) per tile
-constexpr int GEMM_BK = 64;                  // k per stage block
+constexpr int GEMM_BN = 128;                 // output rows (weight rows) per tile = UMMA M
+constexpr int GEMM_BK = 64;                  // k per stage block (4 x UMMA K=16)
 constexpr int GEMM_WBYTES = GEMM_BN * GEMM_BK * 2;   // 16 KB
 constexpr int GEMM_ABYTES = 16 * GEMM_BK * 2;        // 2 KB per 16-token tile
-constexpr int GEMM_CONSUMER_WARPS = 8;
-constexpr int GEMM_THREADS = (GEMM_CONSUMER_WARPS + 1) * 32;
+constexpr int GEMM_EPI_WARPS = 4;            // one per TMEM lane quarter
+constexpr int GEMM_EPI_THREADS = GEMM_EPI_WARPS * 32;
+constexpr int GEMM_THREADS = (GEMM_EPI_WARPS + 2) * 32;   // + MMA warp + TMA producer warp
 constexpr int GEMM_MAX_SEG = 8;
 constexpr int GEMM_SMEM_BUDGET = 221184;     // 216 KB for stages
+// canonical K-major no-swizzle strides of the two operands in shared memory
+constexpr uint32_t GEMM_W_LBO = 16 * 128;    // weight stage [k8 chunk 8][row group 16][8 rows][16 B]
+constexpr uint32_t GEMM_W_SBO = 128;
+constexpr uint32_t GEMM_A_LBO = 2 * 128;     // token tile   [k8 chunk 8][row group 2][8 rows][16 B]
+constexpr uint32_t GEMM_A_SBO = 128;
 
 enum OutMode : int {
     OUT_F32 = 0,        // out[m*ldo + n] = y                              (f32 row-major)
@@ -68,9 +78,11 @@ struct GemmParams {
     int nseg;
     int total_blocks;
     int max_contrib;        // workspace slots per tile
-    float* ws;              // [total_tiles][max_contrib][MT*16][128] partial tiles
+    float* ws;              // [total_tiles][max_contrib][128][MT*16] partial tiles
     unsigned* counters;     // [total_tiles], zero between launches
     const int* nrows;       // device: valid token rows
+    uint32_t w_lbo, w_sbo, a_lbo, a_sbo;   // UMMA descriptor strides (bytes)
+    unsigned long long* trace;             // profiling aid: 8 globaltimer stamps of CTA 0 (null in production)
     GemmSeg seg[GEMM_MAX_SEG];
 };
 
@@ -78,7 +90,9 @@ template <int MT>
 struct GemmCfg {
     static constexpr int STAGE_BYTES = GEMM_WBYTES + MT * GEMM_ABYTES;
     static constexpr int NSTAGE = (GEMM_SMEM_BUDGET / STAGE_BYTES) > 12 ? 12 : (GEMM_SMEM_BUDGET / STAGE_BYTES);
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 2 * NSTAGE * 8 + 64;
+    static constexpr int BAR_BYTES = (2 * NSTAGE + 4) * 8 + 16;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + BAR_BYTES + 64;
+    static constexpr int TMEM_COLS = (2 * 16 * MT) < 32 ? 32 : (2 * 16 * MT);   // double-buffered accumulator
 };
 
 __device__ __forceinline__ int gemm_find_seg(const GemmParams& p, int b) {
@@ -88,46 +102,212 @@ __device__ __forceinline__ int gemm_find_seg(const GemmParams& p, int b) {
     return s;
 }
 
-// one (row, two adjacent columns) result -> fused epilogue
-__device__ __forceinline__ void gemm_store2(const GemmSeg& sg, int m, int n, float v0, float v1) {
-    if (n >= sg.N) return;
-    const bool has1 = (n + 1) < sg.N;
-    if (sg.bias) {
-        v0 += sg.bias[n];
-        if (has1) v1 += sg.bias[n + 1];
+struct RingPos {
+    int stage;
+    uint32_t phase;
+    template <int NSTAGE>
+    __device__ __forceinline__ void advance(int n) {
+        stage += n;
+        while (stage >= NSTAGE) { stage -= NSTAGE; phase ^= 1u; }
     }
-    v0 = apply_act(v0, sg.act);
-    v1 = apply_act(v1, sg.act);
-    if (sg.out_mode == OUT_F32) {
-        float* o = reinterpret_cast<float*>(sg.out) + (size_t)m * sg.ldo + n;
-        if (has1 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
-            *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
-        } else {
-            o[0] = v0;
-            if (has1) o[1] = v1;
+};
+
+// a CTA's block range decomposes into "tile segments": its share of consecutive output tiles
+struct SegWalk {
+    const GemmParams* p;
+    int b, b1, seg, tile_local, kb;
+    __device__ __forceinline__ void init(const GemmParams& p_, int b0, int b1_) {
+        p = &p_; b = b0; b1 = b1_;
+        seg = gemm_find_seg(p_, b0);
+        const GemmSeg& sg = p_.seg[seg];
+        tile_local = (b0 - sg.blk_begin) / sg.KB;
+        kb = (b0 - sg.blk_begin) - tile_local * sg.KB;
+    }
+    __device__ __forceinline__ bool done() const { return b >= b1; }
+    __device__ __forceinline__ int nblk() const { return min(p->seg[seg].KB - kb, b1 - b); }
+    __device__ __forceinline__ void next() {
+        const GemmSeg& sg = p->seg[seg];
+        const int n = nblk();
+        b += n;
+        kb += n;
+        if (kb == sg.KB) {
+            kb = 0;
+            if (++tile_local == sg.tiles) {
+                tile_local = 0;
+                if (seg + 1 < p->nseg) ++seg;
+            }
         }
-        return;
     }
-    if (sg.out_mode == OUT_LERP_A16) {
-        const size_t a = (size_t)m * sg.ld_aux + n;
-        v0 = sg.aux0[a] + sg.aux1[a] * (sg.aux2[n] + v0);
-        if (has1) v1 = sg.aux0[a + 1] + sg.aux1[a + 1] * (sg.aux2[n + 1] + v1);
-    }
-    __half* base = reinterpret_cast<__half*>(sg.out);
-    int nn = n;
-    if (sg.grp > 0) {
-        const int gi = n / sg.grp;
-        base += (size_t)gi * sg.grp_stride;
-        nn = n - gi * sg.grp;
-    }
-    __half* o = base + a16_index(m, nn, sg.ldo);
-    if (has1) {
-        *reinterpret_cast<uint32_t*>(o) = pack_h2(v0, v1);    // n even -> 4-byte aligned, same 32-block
-    } else {
-        o[0] = f2h_sat(v0);
+};
+
+// ---------------------------------------------------------------------------------------
+// MMA role (one thread): consume ring stages, accumulate each tile segment in TMEM.
+// ---------------------------------------------------------------------------------------
+template <int MT, int NSTAGE, int STAGE_BYTES>
+__device__ __forceinline__ void gemm_mma_role(const GemmParams& p, const int b0, const int b1, const uint32_t smem_base,
+                                              const uint32_t full_bar, const uint32_t empty_bar, const uint32_t tfull_bar,
+                                              const uint32_t tempty_bar, const uint32_t tmem_base, RingPos& rp, unsigned& segcount) {
+    constexpr uint32_t IDESC = umma_idesc_f16(GEMM_BN, 16);
+    const uint32_t w_lbo = p.w_lbo, w_sbo = p.w_sbo, a_lbo = p.a_lbo, a_sbo = p.a_sbo;
+    SegWalk w;
+    w.init(p, b0, b1);
+    while (!w.done()) {
+        const int nblk = w.nblk();
+        const unsigned acc = segcount & 1u, use = segcount >> 1;
+        if (use > 0) mbar_wait(tempty_bar + acc * 8, (use - 1) & 1u);     // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * (16 * MT);
+        for (int i = 0; i < nblk; ++i) {
+            mbar_wait(full_bar + rp.stage * 8, rp.phase);
+            tc_fence_after();
+            const uint32_t st = smem_base + rp.stage * STAGE_BYTES;
+#pragma unroll
+            for (int k16 = 0; k16 < GEMM_BK / 16; ++k16) {
+                const uint64_t adesc = umma_desc(st + k16 * 2 * w_lbo, w_lbo, w_sbo);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const uint64_t bdesc = umma_desc(st + GEMM_WBYTES + mt * GEMM_ABYTES + k16 * 2 * a_lbo, a_lbo, a_sbo);
+                    tc_mma_f16(d0 + mt * 16, adesc, bdesc, IDESC, (i > 0 || k16 > 0) ? 1u : 0u);
+                }
+            }
+            tc_commit(empty_bar + rp.stage * 8);          // slot is free once these MMAs have read it
+            rp.advance<NSTAGE>(1);
+        }
+        tc_commit(tfull_bar + acc * 8);                   // accumulator complete -> epilogue
+        ++segcount;
+        w.next();
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Epilogue role (4 warps = 128 threads, thread t owns output row t of the tile): drain TMEM,
+// deterministic cross-CTA reduction of split tiles, fused epilogue.
+// ---------------------------------------------------------------------------------------
+template <int MT>
+__device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const int cta, const int G, const int b0, const int b1,
+                                                   const uint32_t tfull_bar, const uint32_t tempty_bar, const uint32_t tmem_base,
+                                                   unsigned& segcount, const int nrows, volatile int* s_last_p,
+                                                   unsigned long long* tr = nullptr) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned TB = (unsigned)p.total_blocks;
+    auto stamp = [&](int i) {
+        if (tr && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            tr[i] = t;
+        }
+    };
+    SegWalk w;
+    w.init(p, b0, b1);
+    while (!w.done()) {
+        const GemmSeg& sg = p.seg[w.seg];
+        const unsigned acc = segcount & 1u, use = segcount >> 1;
+        mbar_wait(tfull_bar + acc * 8, use & 1u);
+        stamp(8);
+        tc_fence_after();
+        float v[MT][16];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + acc * (16 * MT) + mt * 16, v[mt]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar + acc * 8);     // TMEM buffer may be overwritten
+        ++segcount;
+        stamp(9);
+
+        const unsigned tb0 = (unsigned)(sg.blk_begin + w.tile_local * sg.KB);
+        const int c_first = (int)(((unsigned long long)(tb0 + 1) * (unsigned)G - 1) / TB);
+        const int c_last = (int)(((unsigned long long)(tb0 + sg.KB) * (unsigned)G - 1) / TB);
+        const int ncontrib = c_last - c_first + 1;
+        const int gtile = sg.tile_begin + w.tile_local;
+        bool do_epilogue = true;
+        if (ncontrib > 1) {
+            constexpr int ROWF = 16 * MT;
+            float* wsl = p.ws + ((size_t)gtile * p.max_contrib + (cta - c_first)) * (GEMM_BN * ROWF) + (size_t)tid * ROWF;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4*>(wsl + mt * 16 + j) = make_float4(v[mt][j], v[mt][j + 1], v[mt][j + 2], v[mt][j + 3]);
+            // publish: the barrier orders every thread's partial stores before thread 0's gpu-scope
+            // fence (fences are cumulative), then one counter bump per CTA
+            named_bar_sync(3, GEMM_EPI_THREADS);
+            if (tid == 0) {
+                const unsigned old = atom_add_acq_rel_gpu(p.counters + gtile, 1u);   // release ours, acquire the others'
+                *s_last_p = (old == (unsigned)(ncontrib - 1));
+                if (*s_last_p) p.counters[gtile] = 0;  // ready for the next launch
+            }
+            named_bar_sync(3, GEMM_EPI_THREADS);
+            do_epilogue = (*s_last_p != 0);
+            if (do_epilogue) {
+                const float* ws0 = p.ws + (size_t)gtile * p.max_contrib * (GEMM_BN * ROWF) + (size_t)tid * ROWF;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[mt][j] = 0.f;
+                for (int s = 0; s < ncontrib; ++s) {           // fixed order -> deterministic
+                    const float* w_ = ws0 + (size_t)s * (GEMM_BN * ROWF);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 a = __ldcg(reinterpret_cast<const float4*>(w_ + mt * 16 + j));
+                            v[mt][j] += a.x; v[mt][j + 1] += a.y; v[mt][j + 2] += a.z; v[mt][j + 3] += a.w;
+                        }
+                }
+            }
+        }
+        stamp(10);
+        if (do_epilogue) {
+            // The segment descriptor lives in kernel-parameter space (stand-alone kernel) or global
+            // memory (whole-step kernel): hoist every field the loop needs into registers once.
+            const int n = w.tile_local * GEMM_BN + tid;
+            const int segN = sg.N, out_mode = sg.out_mode, act = sg.act, ldo = sg.ldo, grp = sg.grp, grp_stride = sg.grp_stride;
+            const int ld_aux = sg.ld_aux;
+            void* const outp = sg.out;
+            const float* const biasp = sg.bias;
+            const float* const aux0 = sg.aux0;
+            const float* const aux1 = sg.aux1;
+            const float* const aux2 = sg.aux2;
+            if (n < segN) {
+                const float bias = biasp ? biasp[n] : 0.f;
+                float lv[MT * 16];                     // dynamically indexed below -> local memory, rolled loop
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) lv[mt * 16 + j] = v[mt][j];
+                const int mmax = min(nrows, MT * 16);
+                if (out_mode == OUT_F32) {
+                    float* o = reinterpret_cast<float*>(outp) + n;
+#pragma unroll 1
+                    for (int m = 0; m < mmax; ++m) o[(size_t)m * ldo] = apply_act(lv[m] + bias, act);
+                } else {
+                    __half* base = reinterpret_cast<__half*>(outp);
+                    int nn = n;
+                    if (grp > 0) {
+                        const int gi = n / grp;
+                        base += (size_t)gi * grp_stride;
+                        nn = n - gi * grp;
+                    }
+                    const float mu = (out_mode == OUT_LERP_A16) ? aux2[n] : 0.f;
+#pragma unroll 1
+                    for (int m = 0; m < mmax; ++m) {
+                        float y = apply_act(lv[m] + bias, act);
+                        if (out_mode == OUT_LERP_A16) {
+                            const size_t a_ = (size_t)m * ld_aux + n;
+                            y = aux0[a_] + aux1[a_] * (mu + y);
+                        }
+                        base[a16_index(m, nn, ldo)] = f2h_sat(y);
+                    }
+                }
+            }
+        }
+        w.next();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// stand-alone kernel: warps 0-3 epilogue, warp 4 MMA issuer (+ TMEM allocation), warp 5 TMA producer
+// ---------------------------------------------------------------------------------------
 template <int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<MT>;
@@ -136,23 +316,45 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_bar = smem_base + Cfg::NSTAGE * Cfg::STAGE_BYTES;
     const uint32_t empty_bar = full_bar + Cfg::NSTAGE * 8;
+    const uint32_t tfull_bar = empty_bar + Cfg::NSTAGE * 8;
+    const uint32_t tempty_bar = tfull_bar + 2 * 8;
+    const uint32_t tmem_slot = tempty_bar + 2 * 8;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long TB = p.total_blocks;
     const int G = gridDim.x, cta = blockIdx.x;
     const int b0 = (int)((long long)cta * TB / G);
     const int b1 = (int)((long long)(cta + 1) * TB / G);
+    unsigned long long* const tr = (p.trace && cta == 0) ? p.trace : nullptr;
+    auto stamp = [&](int i) {
+        if (tr) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            tr[i] = t;
+        }
+    };
 
     if (tid == 0) {
+        stamp(0);
         for (int s = 0; s < Cfg::NSTAGE; ++s) {
             mbar_init(full_bar + s * 8, 1);
-            mbar_init(empty_bar + s * 8, GEMM_CONSUMER_WARPS);
+            mbar_init(empty_bar + s * 8, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull_bar + s * 8, 1);
+            mbar_init(tempty_bar + s * 8, GEMM_EPI_WARPS);
         }
         mbar_fence_init();
     }
+    if (warp == GEMM_EPI_WARPS) tc_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+    if (tid == 0) stamp(1);
+    pdl_launch_dependents();     // let the next kernel's CTAs queue up and prefetch their weights
 
-    if (warp == GEMM_CONSUMER_WARPS) {
+    if (warp == GEMM_EPI_WARPS + 1) {
         // ===================== producer: one lane streams stage blocks =====================
         if (lane == 0) {
             const uint64_t pol_w = l2_policy_evict_first();
@@ -167,145 +369,63 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                 bulk_g2s_hint(st, p.W + (size_t)(b0 + i) * GEMM_WBYTES, GEMM_WBYTES, full_bar + i * 8, pol_w);
             }
             pdl_wait();
+            stamp(2);
             int seg = gemm_find_seg(p, b0);
+            const GemmSeg* sg = &p.seg[seg];
+            int kb = (b0 - sg->blk_begin) % sg->KB;
+            int blocks_left_in_seg = sg->blk_begin + sg->tiles * sg->KB - b0;
+            int stage = 0;
+            uint32_t ephase = 1;            // parity of the "previous" phase of the empty barriers
             for (int b = b0, it = 0; b < b1; ++b, ++it) {
-                while (seg + 1 < p.nseg && b >= p.seg[seg + 1].blk_begin) ++seg;
-                const GemmSeg& sg = p.seg[seg];
-                const int kb = (b - sg.blk_begin) % sg.KB;
-                const int stage = it % Cfg::NSTAGE;
                 const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
                 const uint32_t fb = full_bar + stage * 8;
                 if (it >= Cfg::NSTAGE) {
-                    mbar_wait(empty_bar + stage * 8, ((it / Cfg::NSTAGE) - 1) & 1);
+                    mbar_wait(empty_bar + stage * 8, ephase);
                     mbar_expect_tx(fb, Cfg::STAGE_BYTES);
                     bulk_g2s_hint(st, p.W + (size_t)b * GEMM_WBYTES, GEMM_WBYTES, fb, pol_w);
                 }
-                const int kq_tile = sg.KB * 2;
+                const int k8_tile = sg->KB * 8;       // 16-byte k chunks per token tile
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
                     bulk_g2s_hint(st + GEMM_WBYTES + mt * GEMM_ABYTES,
-                                  sg.A + ((size_t)mt * kq_tile + 2 * kb) * 512, GEMM_ABYTES, fb, pol_a);
+                                  sg->A + ((size_t)mt * k8_tile + 8 * kb) * 128, GEMM_ABYTES, fb, pol_a);
+                if (++stage == Cfg::NSTAGE) { stage = 0; ephase ^= 1; }
+                if (++kb == sg->KB) kb = 0;
+                if (--blocks_left_in_seg == 0 && b + 1 < b1) {
+                    ++seg;
+                    sg = &p.seg[seg];
+                    kb = 0;
+                    blocks_left_in_seg = sg->tiles * sg->KB;
+                }
             }
         }
-        return;
+    } else if (warp == GEMM_EPI_WARPS) {
+        // ===================== MMA issuer: one lane =====================
+        if (lane == 0) {
+            RingPos rp{0, 0u};
+            unsigned segcount = 0;
+            if (tr) { mbar_wait(full_bar, 0); stamp(3); }
+            gemm_mma_role<MT, Cfg::NSTAGE, Cfg::STAGE_BYTES>(p, b0, b1, smem_base, full_bar, empty_bar, tfull_bar, tempty_bar,
+                                                             tmem_base, rp, segcount);
+            stamp(4);
+        }
+    } else {
+        // ===================== epilogue: 4 warps =====================
+        pdl_wait();
+        if (tid == 0) stamp(5);
+        unsigned segcount = 0;
+        gemm_epilogue_role<MT>(p, cta, G, b0, b1, tfull_bar, tempty_bar, tmem_base, segcount, *p.nrows, &s_last, tr);
+        if (tid == 0) stamp(6);
     }
-
-    // ============================== consumers: 8 warps =====================================
-    pdl_wait();
-    const int nrows = *p.nrows;
-    const int g = lane >> 2, q = lane & 3;
-    float acc[MT][2][4];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[mt][j][e] = 0.f;
-
-    int seg = gemm_find_seg(p, b0);
-    for (int b = b0, it = 0; b < b1; ++b, ++it) {
-        while (seg + 1 < p.nseg && b >= p.seg[seg + 1].blk_begin) ++seg;
-        const GemmSeg& sg = p.seg[seg];
-        const int rel = b - sg.blk_begin;
-        const int tile_local = rel / sg.KB;
-        const int kb = rel - tile_local * sg.KB;
-        const int stage = it % Cfg::NSTAGE;
-        const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
-        mbar_wait(full_bar + stage * 8, (it / Cfg::NSTAGE) & 1);
-#pragma unroll
-        for (int kq = 0; kq < 2; ++kq) {
-            uint4 wv[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) wv[j] = lds128(st + (((warp * 2 + j) * 2 + kq) * 512) + lane * 16);
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const uint32_t ab = st + GEMM_WBYTES + mt * GEMM_ABYTES + kq * 1024 + lane * 16;
-                const uint4 alo = lds128(ab);          // token row g,   k chunk q
-                const uint4 ahi = lds128(ab + 512);    // token row g+8, k chunk q
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    mma_16816(acc[mt][j], alo.x, ahi.x, alo.y, ahi.y, wv[j].x, wv[j].y);
-                    mma_16816(acc[mt][j], alo.z, ahi.z, alo.w, ahi.w, wv[j].z, wv[j].w);
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_bar + stage * 8);
-
-        if (kb == sg.KB - 1 || b == b1 - 1) {
-            // ---- this CTA's share of the tile is complete ----
-            const long long tb0 = (long long)sg.blk_begin + (long long)tile_local * sg.KB;
-            const int c_first = (int)(((tb0 + 1) * G - 1) / TB);
-            const int c_last = (int)(((tb0 + sg.KB) * G - 1) / TB);
-            const int ncontrib = c_last - c_first + 1;
-            const int gtile = sg.tile_begin + tile_local;
-            bool do_epilogue = true;
-            if (ncontrib > 1) {
-                float* wsl = p.ws + ((size_t)gtile * p.max_contrib + (cta - c_first)) * (MT * 16 * GEMM_BN);
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int col = (warp * 2 + j) * 8 + 2 * q;
-                        *reinterpret_cast<float2*>(wsl + (mt * 16 + g) * GEMM_BN + col) =
-                            make_float2(acc[mt][j][0], acc[mt][j][1]);
-                        *reinterpret_cast<float2*>(wsl + (mt * 16 + g + 8) * GEMM_BN + col) =
-                            make_float2(acc[mt][j][2], acc[mt][j][3]);
-                    }
-                __threadfence();
-                named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
-                if (tid == 0) {
-                    const unsigned old = atomicAdd(p.counters + gtile, 1u);
-                    s_last = (old == (unsigned)(ncontrib - 1));
-                    if (s_last) p.counters[gtile] = 0;     // ready for the next launch
-                }
-                named_bar_sync(1, GEMM_CONSUMER_WARPS * 32);
-                do_epilogue = (s_last != 0);
-                if (do_epilogue) {
-                    __threadfence();
-                    const float* ws0 = p.ws + (size_t)gtile * p.max_contrib * (MT * 16 * GEMM_BN);
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int col = (warp * 2 + j) * 8 + 2 * q;
-                            float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
-                            for (int s = 0; s < ncontrib; ++s) {   // fixed order -> deterministic
-                                const float* w_ = ws0 + (size_t)s * (MT * 16 * GEMM_BN);
-                                const float2 a = __ldcg(reinterpret_cast<const float2*>(w_ + (mt * 16 + g) * GEMM_BN + col));
-                                const float2 c = __ldcg(reinterpret_cast<const float2*>(w_ + (mt * 16 + g + 8) * GEMM_BN + col));
-                                lo.x += a.x; lo.y += a.y; hi.x += c.x; hi.y += c.y;
-                            }
-                            acc[mt][j][0] = lo.x; acc[mt][j][1] = lo.y;
-                            acc[mt][j][2] = hi.x; acc[mt][j][3] = hi.y;
-                        }
-                }
-                // s_last is rewritten only after the next pair of barriers: safe to fall through
-            }
-            if (do_epilogue) {
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int n = tile_local * GEMM_BN + (warp * 2 + j) * 8 + 2 * q;
-                        const int m0 = mt * 16 + g;
-                        if (m0 < nrows) gemm_store2(sg, m0, n, acc[mt][j][0], acc[mt][j][1]);
-                        if (m0 + 8 < nrows) gemm_store2(sg, m0 + 8, n, acc[mt][j][2], acc[mt][j][3]);
-                    }
-            }
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[mt][j][e] = 0.f;
-        }
-    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) stamp(7);
+    if (warp == GEMM_EPI_WARPS) tc_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------
-// One-time weight re-tiling:  W[N, K] row-major f16  ->  stage blocks
-//   block(tile, kb) = [nb 16][kq 2][row 8][k 32] halves, zero padded.
+// One-time weight re-tiling:  W[N, K] row-major f16  ->  stage blocks in the UMMA canonical
+// K-major / no-swizzle layout:  block(tile, kb) = [k8 chunk 8][row group 16][row 8][8 halves], zero padded.
 // Supports a row-parallel / column-parallel shard: source sub-matrix rows [n0, n0+N), cols [k0, k0+K)
 // of a matrix with row stride ld.
 // ---------------------------------------------------------------------------------------
@@ -315,14 +435,13 @@ __global__ void repack_weight_kernel(const __half* __restrict__ src, int ld, int
     const size_t nchunk = (size_t)tiles * KB * (GEMM_WBYTES / 16);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nchunk; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
-        const int c8 = r % 4; r /= 4;        // 8-half chunk within the 32-k row
-        const int row = r % 8; r /= 8;
-        const int kq = r % 2; r /= 2;
-        const int nb = r % 16; r /= 16;
+        const int row = r % 8; r /= 8;       // row inside the 8-row core matrix
+        const int mi = r % 16; r /= 16;      // row group
+        const int kj = r % 8; r /= 8;        // 8-half (16-byte) k chunk
         const int kb = r % KB; r /= KB;
         const int tile = (int)r;
-        const int n = tile * GEMM_BN + nb * 8 + row;
-        const int k = kb * GEMM_BK + kq * 32 + c8 * 8;
+        const int n = tile * GEMM_BN + mi * 8 + row;
+        const int k = kb * GEMM_BK + kj * 8;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (n < N) {
             const __half* s = src + (size_t)(n0 + n) * ld + k0 + k;

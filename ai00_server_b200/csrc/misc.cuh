@@ -14,10 +14,10 @@ __global__ void __launch_bounds__(1024) softmax_kernel(const float* __restrict__
     float* y = out + (size_t)blockIdx.x * V;
     float mx = -INFINITY;
     for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, x[i]);
-    mx = block_max(mx, red);
+    mx = block_max_any(mx, red);
     float s = 0.f;
     for (int i = threadIdx.x; i < V; i += blockDim.x) s += expf(x[i] - mx);
-    s = block_sum(s, red);
+    s = block_sum_any(s, red);
     const float inv = 1.0f / s;
     for (int i = threadIdx.x; i < V; i += blockDim.x) y[i] = expf(x[i] - mx) * inv;
 }

@@ -1,0 +1,105 @@
+// Streaming micro-benchmarks (debug entry point b200rwkv_debug_stream): how fast can one B200 pull
+// a large buffer from HBM through (a) plain vector loads, (b) the 1-D bulk-TMA stage ring used by
+// the projection GEMM with a trivial consumer, (c) the same ring drained by tcgen05.mma.
+// Not on the product path; used to size the ring and to separate producer limits from consumer limits.
+#pragma once
+#include "gemm.cuh"
+
+namespace b200 {
+
+__global__ void __launch_bounds__(256) stream_ldg_kernel(const uint4* __restrict__ src, size_t n16, unsigned* sink) {
+    unsigned acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 7 * stride < n16; i += 8 * stride) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcs(src + i + j * stride);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc ^= v[j].x ^ v[j].y ^ v[j].z ^ v[j].w;
+    }
+    if (acc == 0x12345u) *sink = acc;
+}
+
+struct StreamParams {
+    const uint8_t* src;
+    size_t bytes_per_cta;
+    int stage_bytes;     // multiple of 1024
+    int nstage;
+    int use_hint;        // 0 none, 1 evict_first
+    int consumer;        // 0 trivial (wait + arrive), 1 tcgen05.mma over the stage, 2 = 1 with commit only every stage
+    int split;           // bulk copies per stage (1, 2, 4)
+    int producers;       // producer warps issuing in round robin (1..3)
+    int extra;           // bytes of the stage sent as a separate small copy (the GEMM's activation slice)
+};
+
+// one CTA per SM, warp 0 lanes = producers, warp 1 lane 0 = consumer
+__global__ void __launch_bounds__(128, 1) stream_ring_kernel(const __grid_constant__ StreamParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t smem_base = smem_u32(smem);
+    const int NS = p.nstage, SB = p.stage_bytes;
+    const uint32_t full_bar = smem_base + NS * SB;
+    const uint32_t empty_bar = full_bar + NS * 8;
+    const uint32_t tmem_slot = empty_bar + NS * 8;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(full_bar + s * 8, 1); mbar_init(empty_bar + s * 8, 1); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tc_alloc(tmem_slot, 32);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + (tmem_slot - smem_base));
+    const size_t nst = p.bytes_per_cta / SB;
+    const uint8_t* src = p.src + (size_t)blockIdx.x * p.bytes_per_cta;
+    // producers: lane 0 of warps 0, 2, 3 (round robin over stages); consumer: lane 0 of warp 1
+    const int prod_id = (warp == 0) ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
+    if (prod_id >= 0 && prod_id < p.producers && lane == 0) {
+        const uint64_t pol = l2_policy_evict_first();
+        const int piece = (SB - p.extra) / p.split;
+        int stage = prod_id;
+        uint32_t par = 1;                 // parity of the previous use
+        while (stage >= NS) { stage -= NS; par ^= 1u; }
+        unsigned seq = prod_id;
+        for (size_t it = prod_id; it < nst; it += p.producers, seq += p.producers) {
+            if (seq >= (unsigned)NS) mbar_wait(empty_bar + stage * 8, par);
+            mbar_expect_tx(full_bar + stage * 8, SB);
+            const uint8_t* g = src + it * (size_t)SB;
+            for (int s_ = 0; s_ < p.split; ++s_) {
+                if (p.use_hint) bulk_g2s_hint(smem_base + stage * SB + s_ * piece, g + (size_t)s_ * piece, piece, full_bar + stage * 8, pol);
+                else bulk_g2s(smem_base + stage * SB + s_ * piece, g + (size_t)s_ * piece, piece, full_bar + stage * 8);
+            }
+            if (p.extra) bulk_g2s(smem_base + stage * SB + (SB - p.extra), g + (SB - p.extra), p.extra, full_bar + stage * 8);
+            stage += p.producers;
+            while (stage >= NS) { stage -= NS; par ^= 1u; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        constexpr uint32_t IDESC = umma_idesc_f16(128, 16);
+        int stage = 0;
+        uint32_t par = 0;
+        for (size_t it = 0; it < nst; ++it) {
+            mbar_wait(full_bar + stage * 8, par);
+            if (p.consumer == 0) {
+                mbar_arrive(empty_bar + stage * 8);
+            } else {
+                tc_fence_after();
+                const uint32_t st = smem_base + stage * SB;
+                for (int blk = 0; blk < SB / 16384; ++blk)
+                    for (int k16 = 0; k16 < 4; ++k16) {
+                        const uint64_t a_ = umma_desc(st + blk * 16384 + k16 * 2 * GEMM_W_LBO, GEMM_W_LBO, GEMM_W_SBO);
+                        const uint64_t b_ = umma_desc(st + k16 * 2 * GEMM_A_LBO, GEMM_A_LBO, GEMM_A_SBO);   // garbage operand, same smem
+                        tc_mma_f16(tmem_base, a_, b_, IDESC, 1u);
+                    }
+                tc_commit(empty_bar + stage * 8);
+            }
+            if (it + 1 == nst && p.consumer != 0) mbar_wait(empty_bar + stage * 8, par);   // all MMAs retired
+            if (++stage == NS) { stage = 0; par ^= 1u; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc_dealloc(tmem_base, 32);
+}
+
+}  // namespace b200

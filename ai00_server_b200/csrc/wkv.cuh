@@ -5,20 +5,24 @@
 // dispatches under `Runtime::infer` (reference run.rs:1143; SURVEY.md §2.2 K6/K6'/K7, math in
 // App. A / App. B).
 //
-// One CTA per (head, active slot).  The 64x64 f32 head state (16 KB) lives in HBM as
+// One 256-thread group per (head, slot).  The 64x64 f32 head state (16 KB) lives in HBM as
 // M[value][key] for every version (v6's S[key][value] is stored transposed; the API layout is
 // restored by the state import/export kernels), so that
-//   * each thread owns a 4(value) x 4(key) patch: 4 coalesced 16-byte loads, rows read as full
-//     256-byte runs, 16 KB per CTA in flight, ~5 CTAs per SM;
+//   * each thread owns a 4(value) x 4(key) patch: 4 coalesced 16-byte accesses, rows moved as full
+//     256-byte runs;
 //   * every reduction of the recurrence runs over the KEY index = across the 16 lanes of a
 //     half-warp -> pure shuffles, no shared-memory round trip:
 //       v5/v6: out[v] = sum_k r[k] * (u[k] k[k] v[v] + M[v][k]);  M[v][k] = k[k] v[v] + w[k] M[v][k]
 //       v7:    sa[v]  = sum_k M[v][k] * (-kk[k]);
 //              M[v][k] = M[v][k] w[k] + sa[v] (kk[k] a[k]) + v[v] k[k];   out[v] = sum_k M[v][k] r[k]
-//   * state is read once and written once per step (streaming cache hints), the recurrence
-//     loops over the slot's tokens with the state in registers (prefill chunks).
+//   * state is read once and written once per step, the recurrence loops over the slot's tokens
+//     with the state in registers (prefill chunks).
 // Output: f16( GroupNorm(out) [+ bonus] * gate ) written straight into the A16 operand of the
 // output projection.
+//
+// Two callers share `wkv_slot`: the stand-alone kernel below (one CTA per (head, slot), state
+// through coalesced vector loads) and the persistent whole-step kernel (mega.cuh), where the
+// state tiles arrive through the bulk-TMA stage ring and the v6 decay LoRA is evaluated in place.
 #pragma once
 #include "common.cuh"
 
@@ -53,37 +57,34 @@ struct WkvParams {
     const float* r_k;
     __half* out;            // A16 [T, ld]
     int kq_tile;
+    // v6, whole-step kernel only: decay LoRA stage 2 evaluated inside the WKV phase
+    const __half* wd2t;     // [H][Dd][64] f16: time_decay_w2 rows of each head, k-major
+    const float* decay_bias;    // [ld] time_decay
+    const __half* d1;       // A16 [T, Dd]: tanh(time_decay_w1 @ xw)
+    int d1_kq;
+    int Dd;
 };
 
-template <int VER>
-__global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant__ WkvParams p) {
-    __shared__ float s_r[WKV_N], s_k[WKV_N], s_v[WKV_N], s_w[WKV_N], s_b[WKV_N], s_o[WKV_N];
-    __shared__ float s_red[4];
-    pdl_launch_dependents();
-    const int si = blockIdx.y;
-    const int h = blockIdx.x;
+struct WkvShared {
+    float r[WKV_N], k[WKV_N], v[WKV_N], w[WKV_N], b[WKV_N], o[WKV_N];
+    float red[4];
+};
+
+// Runs the recurrence for `nt` tokens starting at token index t0 on head h with the state patch
+// m[4] (rows 4*ig+e, cols 4*j4..) in registers.  `w_local`: optional shared-memory decay rows
+// [token][64] (whole-step kernel, v6) indexed from local token `lt0`.
+template <int VER, bool MEGA>
+__device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const int t0, const int nt, float4 (&m)[4],
+                                         WkvShared& sm, const float* w_local, const int lt0) {
     const int tid = threadIdx.x;
     const int ig = tid >> 4;           // value rows 4*ig .. 4*ig+3
     const int j4 = tid & 15;           // key cols  4*j4 .. 4*j4+3
-
-    pdl_wait();
-    if (si >= p.meta.nslots()) return;
-    const int slot = p.meta.slot_id()[si];
-    const int t0 = p.meta.slot_start()[si];
-    const int nt = p.meta.slot_count()[si];
-
-    float* M = p.state + ((size_t)slot * p.H + h) * (WKV_N * WKV_N);
-    float4 m[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) m[e] = __ldcs(reinterpret_cast<const float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4));
-
     const int ch = h * WKV_N;          // channel base of this head
     float u4[4] = {0.f, 0.f, 0.f, 0.f};
     if (VER != 7) {
 #pragma unroll
         for (int f = 0; f < 4; ++f) u4[f] = p.u[ch + j4 * 4 + f];
     }
-
     for (int tt = 0; tt < nt; ++tt) {
         const int t = t0 + tt;
         const size_t row = (size_t)t * p.ld + ch;
@@ -93,36 +94,37 @@ __global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant_
             float r = p.r[row + c], k = p.k[row + c], v = p.v[row + c];
             float w;
             if (VER == 5) w = p.w_static[ch + c];
+            else if (w_local) w = w_local[(lt0 + tt) * WKV_N + c];
             else w = p.w[row + c];
             if (VER == 7) {
                 const float a = p.a[row + c];
                 float kk = k * p.k_k[ch + c];
                 // l2 norm over the head: two warps
                 float ss = warp_sum(kk * kk);
-                if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+                if ((tid & 31) == 0) sm.red[tid >> 5] = ss;
                 asm volatile("bar.sync 2, 64;" ::: "memory");
-                ss = s_red[0] + s_red[1];
+                ss = sm.red[0] + sm.red[1];
                 kk = kk / fmaxf(sqrtf(ss), 1e-12f);
                 k = k * (1.f + (a - 1.f) * p.k_a[ch + c]);
                 if (p.layer0) p.v_first[row + c] = v;
                 else v = v + (p.v_first[row + c] - v) * p.nu[row + c];
                 float bonus = warp_sum(r * k * p.r_k[ch + c]);
-                if ((tid & 31) == 0) s_red[2 + (tid >> 5)] = bonus;
-                s_b[c] = kk * a;        // kk (.) a
-                s_o[c] = -kk;           // reuse s_o as -kk until the output phase
+                if ((tid & 31) == 0) sm.red[2 + (tid >> 5)] = bonus;
+                sm.b[c] = kk * a;       // kk (.) a
+                sm.o[c] = -kk;          // reuse o as -kk until the output phase
             }
-            s_r[c] = r; s_k[c] = k; s_v[c] = v; s_w[c] = w;
+            sm.r[c] = r; sm.k[c] = k; sm.v[c] = v; sm.w[c] = w;
         }
-        __syncthreads();
+        cta_sync<MEGA>();
 
         float rr[4], kk_[4], ww[4];
 #pragma unroll
-        for (int f = 0; f < 4; ++f) { rr[f] = s_r[j4 * 4 + f]; kk_[f] = s_k[j4 * 4 + f]; ww[f] = s_w[j4 * 4 + f]; }
+        for (int f = 0; f < 4; ++f) { rr[f] = sm.r[j4 * 4 + f]; kk_[f] = sm.k[j4 * 4 + f]; ww[f] = sm.w[j4 * 4 + f]; }
         float o[4];
         if (VER != 7) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float vv = s_v[ig * 4 + e];
+                const float vv = sm.v[ig * 4 + e];
                 float* me = reinterpret_cast<float*>(&m[e]);
                 float acc = 0.f;
 #pragma unroll
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant_
         } else {
             float nk[4], ka[4];
 #pragma unroll
-            for (int f = 0; f < 4; ++f) { nk[f] = s_o[j4 * 4 + f]; ka[f] = s_b[j4 * 4 + f]; }
+            for (int f = 0; f < 4; ++f) { nk[f] = sm.o[j4 * 4 + f]; ka[f] = sm.b[j4 * 4 + f]; }
             float sa[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant_
                 for (int e = 0; e < 4; ++e) sa[e] += __shfl_xor_sync(0xffffffffu, sa[e], off);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float vv = s_v[ig * 4 + e];
+                const float vv = sm.v[ig * 4 + e];
                 float* me = reinterpret_cast<float*>(&m[e]);
                 float acc = 0.f;
 #pragma unroll
@@ -164,16 +166,16 @@ __global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant_
         for (int off = 8; off > 0; off >>= 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], off);
-        __syncthreads();               // all reads of s_o (-kk) done before it is overwritten
+        cta_sync<MEGA>();              // all reads of sm.o (-kk) done before it is overwritten
         if (j4 == 0) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) s_o[ig * 4 + e] = o[e];
+            for (int e = 0; e < 4; ++e) sm.o[ig * 4 + e] = o[e];
         }
-        __syncthreads();
+        cta_sync<MEGA>();
 
         // ---- GroupNorm over the head + gate, warp 0: 2 channels per lane ----
         if (tid < 32) {
-            const float x0 = s_o[tid], x1 = s_o[tid + 32];
+            const float x0 = sm.o[tid], x1 = sm.o[tid + 32];
             const float mean = warp_sum(x0 + x1) * (1.f / WKV_N);
             const float d0 = x0 - mean, d1 = x1 - mean;
             const float var = warp_sum(d0 * d0 + d1 * d1) * (1.f / WKV_N);
@@ -181,18 +183,38 @@ __global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant_
             float y0 = d0 * rstd * p.lnx_w[ch + tid] + p.lnx_b[ch + tid];
             float y1 = d1 * rstd * p.lnx_w[ch + tid + 32] + p.lnx_b[ch + tid + 32];
             if (VER == 7) {
-                const float bonus = s_red[2] + s_red[3];
-                y0 += bonus * s_v[tid];
-                y1 += bonus * s_v[tid + 32];
+                const float bonus = sm.red[2] + sm.red[3];
+                y0 += bonus * sm.v[tid];
+                y1 += bonus * sm.v[tid + 32];
             }
             y0 *= p.g[row + tid];
             y1 *= p.g[row + tid + 32];
             p.out[a16_index(t, ch + tid, p.kq_tile)] = f2h_sat(y0);
             p.out[a16_index(t, ch + tid + 32, p.kq_tile)] = f2h_sat(y1);
         }
-        __syncthreads();               // shared vectors are rewritten by the next token
+        cta_sync<MEGA>();              // shared vectors are rewritten by the next token
     }
+}
 
+template <int VER>
+__global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant__ WkvParams p) {
+    __shared__ WkvShared sm;
+    pdl_launch_dependents();
+    const int si = blockIdx.y;
+    const int h = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int ig = tid >> 4, j4 = tid & 15;
+    pdl_wait();
+    if (si >= p.meta.nslots()) return;
+    const int slot = p.meta.slot_id()[si];
+    const int t0 = p.meta.slot_start()[si];
+    const int nt = p.meta.slot_count()[si];
+
+    float* M = p.state + ((size_t)slot * p.H + h) * (WKV_N * WKV_N);
+    float4 m[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m[e] = __ldcs(reinterpret_cast<const float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4));
+    wkv_slot<VER, false>(p, h, t0, nt, m, sm, nullptr, 0);
 #pragma unroll
     for (int e = 0; e < 4; ++e) __stcs(reinterpret_cast<float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4), m[e]);
 }

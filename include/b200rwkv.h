@@ -145,6 +145,18 @@ int32_t b200rwkv_last_hidden(b200rwkv_engine*, float* out, size_t cap);
  * row-major; returns the column count (negative status on error).  Not on the product path. */
 int32_t b200rwkv_debug_read(b200rwkv_engine*, const char* name, float* out, size_t cap);
 
+/* Profiling aid: per-phase timer stamps of the last whole-step kernel (B200RWKV_TRACE=1). */
+int32_t b200rwkv_debug_trace(b200rwkv_engine*, uint64_t* out, size_t cap, int32_t* types, int32_t* nphase);
+
+/* Profiling aid: one projection launch class timed in isolation over all layers. */
+int32_t b200rwkv_debug_gemm_time(b200rwkv_engine*, int32_t which, int32_t reps, float* ms_out, int64_t* bytes_out,
+                                 uint64_t* trace_out);
+
+/* Profiling aid: HBM streaming micro-benchmark (plain loads vs the bulk-TMA stage ring). */
+int32_t b200rwkv_debug_stream(int32_t device, int32_t kind, double gbytes, int32_t stage_bytes, int32_t nstage,
+                              int32_t use_hint, int32_t consumer, int32_t split, int32_t producers, int32_t reps,
+                              float* ms_out);
+
 const char* b200rwkv_last_error(b200rwkv_engine*);
 
 #ifdef __cplusplus

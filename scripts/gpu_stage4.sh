@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== debug standalone (mega=0)"; B200RWKV_MEGA=0 timeout 180 python scripts/gpu_debug.py tiny6 > gpurun_out/debug_m0.log 2>&1; echo "rc=$?"; grep -E "==|rel" gpurun_out/debug_m0.log | head -24; tail -n 3 gpurun_out/debug_m0.log
+echo "== debug standalone swap"; B200RWKV_UMMA_SWAP=1 B200RWKV_MEGA=0 timeout 180 python scripts/gpu_debug.py tiny6 > gpurun_out/debug_m0s.log 2>&1; echo "rc=$?"; grep -E "==|rel" gpurun_out/debug_m0s.log | head -8
+echo "== debug mega"; timeout 180 python scripts/gpu_debug.py tiny6 tiny7 > gpurun_out/debug_m1.log 2>&1; echo "rc=$?"; grep -E "==|logits|state rel" gpurun_out/debug_m1.log | head -16; tail -n 3 gpurun_out/debug_m1.log
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -n 8 gpurun_out/pytest_gpu.log
+export B200RWKV_BENCH_CPU_STEPS=0
+for mg in 1 0; do
+  echo "== bench 7b mega=$mg"; B200RWKV_MEGA=$mg timeout 600 python bench.py --steps 64 --warmup 4 > gpurun_out/bench_mega$mg.log 2>&1; echo "rc=$?"
+  python - <<PY
+import json
+l=open("gpurun_out/bench_mega$mg.log").read().strip().splitlines()[-1]
+try:
+    d=json.loads(l); r=d["roofline"]; print("mega=$mg ms/step %.3f tok/s %.0f e2e_ms %.3f step_frac %.3f launches %d"%(d["ms_per_step"], d["value"], d["e2e"]["ms_per_step"], r["step_frac"], d["gpu_launches"]))
+except Exception as e: print("ERR", l[-600:])
+PY
+done
+timeout 300 python scripts/gpu_trace.py 2>&1 | tail -12
