@@ -43,6 +43,7 @@ SYMBOLS = [
     ("b200rwkv_create_tp", C.c_int32, [_P, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     ("b200rwkv_tp_export", C.c_int32, [_P, _P]),
     ("b200rwkv_tp_connect", C.c_int32, [_P, _P]),
+    ("b200rwkv_tp_connect_local", C.c_int32, [C.POINTER(_P), C.c_int32]),
     ("b200rwkv_destroy", None, [_P]),
     ("b200rwkv_get_info", C.c_int32, [_P, C.POINTER(Info)]),
     ("b200rwkv_infer", C.c_int32, [_P, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),

@@ -67,15 +67,58 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// ---------------------------------------------------------------------------------------
+// Watchdog: every spin-wait in this library gives up after ~2 s, writes a record to mapped pinned
+// host memory (so it survives the dead context) and traps: a protocol bug becomes a CUDA error
+// with a diagnosis instead of a hung GPU.  g_watchdog is set once per process by the host.
+// record: [0]=0xDEAD0000|code [1]=blockIdx.x [2]=threadIdx.x [3]=arg0 [4]=arg1 [5]=arg2
+// ---------------------------------------------------------------------------------------
+__device__ unsigned* g_watchdog = nullptr;
+constexpr unsigned long long WATCHDOG_NS = 2000000000ull;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ void watchdog_fire(unsigned code, unsigned a0, unsigned a1, unsigned a2) {
+    unsigned* w = g_watchdog;
+    if (w) {
+        w[1] = blockIdx.x; w[2] = threadIdx.x; w[3] = a0; w[4] = a1; w[5] = a2;
+        __threadfence_system();
+        w[0] = 0xDEAD0000u | code;
+        __threadfence_system();
+    }
+    __trap();
+}
+struct SpinGuard {          // poll(): call once per spin iteration
+    unsigned n = 0;
+    unsigned long long t0 = 0;
+    __device__ __forceinline__ void poll(unsigned code, unsigned a0, unsigned a1, unsigned a2) {
+        if ((++n & 0x3FFu) == 0) {
+            const unsigned long long t = globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > ((code == 2u || code == 3u) ? 2 * WATCHDOG_NS : WATCHDOG_NS)) watchdog_fire(code, a0, a1, a2);   // passive waiters (grid barrier, phase start) wait longest: the culprit reports first
+        }
+    }
+};
+enum WatchCode : unsigned { WD_MBAR = 1, WD_GRIDBAR = 2, WD_A_STARTED = 3, WD_A_WSEQ = 4 };
+
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// `tag` identifies the call site in watchdog reports
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned tag = 0) {
+    if (mbar_try(bar, parity)) return;
+    SpinGuard g;
+    while (!mbar_try(bar, parity)) g.poll(WD_MBAR, bar, parity, tag);
 }
 // L2 policy for streamed-once weights
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {

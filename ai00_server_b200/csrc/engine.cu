@@ -3,6 +3,8 @@
 // exists in this image) — see include/b200rwkv.h for the reference call site of every entry.
 #include "../../include/b200rwkv.h"
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -36,7 +38,7 @@ struct Error : std::runtime_error {
         cudaError_t e_ = (call);                                                                         \
         if (e_ != cudaSuccess)                                                                           \
             throw Error(B200RWKV_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" +   \
-                                               __FILE__ + ":" + std::to_string(__LINE__));               \
+                                               __FILE__ + ":" + std::to_string(__LINE__) + watchdog_report()); \
     } while (0)
 #define REQUIRE(cond, code, msg)                 \
     do {                                         \
@@ -44,6 +46,23 @@ struct Error : std::runtime_error {
     } while (0)
 
 static thread_local std::string g_err;
+
+// watchdog record in mapped pinned host memory (see common.cuh)
+static unsigned* g_wd_host = nullptr;
+static void watchdog_setup() {
+    if (g_wd_host) { memset(g_wd_host, 0, 64); return; }
+    unsigned* h = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return;
+    memset(h, 0, 64);
+    g_wd_host = h;
+}
+static std::string watchdog_report() {
+    if (!g_wd_host || (g_wd_host[0] >> 16) != 0xDEADu) return "";
+    char buf[256];
+    snprintf(buf, sizeof buf, " [device watchdog: code=%u block=%u thread=%u a0=0x%x a1=%u a2=%u]", g_wd_host[0] & 0xFFFFu, g_wd_host[1],
+             g_wd_host[2], g_wd_host[3], g_wd_host[4], g_wd_host[5]);
+    return buf;
+}
 
 // =========================================================================================
 // safetensors reader (header = u64 LE length + JSON object; tensor bytes follow)
@@ -297,6 +316,14 @@ struct b200rwkv_engine {
     bool use_mega = true, mega_ok = false;
     MegaParams mega;
     std::vector<int> mega_phase_types;
+    int split_att = 1, split_ffn = 1;
+    // tensor parallel: one symmetric comm block per rank (partials, gate block, logits shard, flags)
+    uint8_t* comm_base = nullptr;
+    size_t comm_bytes = 0, off_part_att = 0, off_part_ffn = 0, off_rr = 0, off_logits = 0, off_flags = 0;
+    uint8_t* peer_base[8] = {nullptr};
+    bool connected = false;
+    TpBar tpbar;
+    unsigned* d_epoch = nullptr;
     int skip_mask = 0;   // timing attribution only (B200RWKV_SKIP): 1 LN, 2 small GEMMs, 4 WKV, 8 big GEMMs, 16 head
     cudaStream_t stream = nullptr, sm_stream = nullptr;
     std::vector<void*> allocs;
@@ -349,8 +376,15 @@ struct b200rwkv_engine {
     const __half* upload_tmp(const StTensor& t);
     float* vec_f32(const StFile& st, const std::string& name, size_t off, size_t count, float scale = 1.f, float bias = 0.f);
     A16Buf a16_alloc(int K, int nmat = 1);
-    GemmLaunch make_launch(std::vector<SegDesc>& segs);
+    GemmLaunch make_launch(std::vector<SegDesc>& segs, int force_grid = 0);
+    int pick_split(int K, int tiles) const;
     void build_mega(const StFile& st);
+    void build_mega_program();
+    void finalize_tp();
+    bool mega_prepared = false, mega_lora_cc = false;
+    std::vector<WkvParams> mega_wkvs;
+    std::vector<SmallNParams> mega_smallns;
+    std::vector<SmallKParams> mega_smallks;
     void launch_mega(cudaStream_t s);
 
     template <typename P>
@@ -410,14 +444,14 @@ float* b200rwkv_engine::vec_f32(const StFile& st, const std::string& name, size_
 
 A16Buf b200rwkv_engine::a16_alloc(int K, int nmat) {
     A16Buf b;
-    const int Kp = rup(K, GEMM_BK);
+    const int Kp = rup(K, GEMM_BK);          // whole 128-wide k blocks, zero padded
     b.kq = Kp / 32;
     b.halves_per_matrix = (size_t)(maxT / 16) * b.kq * 512;
     b.p = (__half*)dalloc(b.halves_per_matrix * 2 * nmat, true);
     return b;
 }
 
-GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs) {
+GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_grid) {
     REQUIRE(!segs.empty() && (int)segs.size() <= GEMM_MAX_SEG, B200RWKV_ERR_INVALID, "internal: bad segment count");
     GemmLaunch g;
     memset(&g.p, 0, sizeof(g.p));
@@ -464,8 +498,9 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs) {
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());   // d_tmp is reused by the next upload
     }
-    g.grid = std::max(1, std::min(num_sms, std::max(tile, cdiv(blk, 8))));
+    g.grid = std::max(1, std::min(num_sms, std::max(tile, cdiv(blk, 4))));
     g.grid = std::min(g.grid, blk);
+    if (force_grid > 0) g.grid = std::min(force_grid, blk);
     const int per_cta = std::max(1, blk / g.grid);
     g.p.max_contrib = cdiv(kbmax, per_cta) + 1;
     g.p.counters = (unsigned*)dalloc((size_t)tile * 4, true);
@@ -513,6 +548,17 @@ void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, P
     }
 }
 
+// static split-K factor of a row-parallel projection: largest S <= 4 (and <= 8 / world partial
+// buffers) that cuts K into whole 128-wide blocks and gives every CTA whole tiles
+int b200rwkv_engine::pick_split(int K, int tiles) const {
+    if (getenv("B200RWKV_NOSPLIT")) return 1;
+    const int kb = K / GEMM_BK;
+    if (K % GEMM_BK != 0) return 1;
+    for (int S = std::min(4, 8 / world); S > 1; --S)
+        if (kb % S == 0 && tiles * S <= num_sms) return S;
+    return 1;
+}
+
 // -----------------------------------------------------------------------------------------
 // model build
 // -----------------------------------------------------------------------------------------
@@ -522,7 +568,7 @@ void b200rwkv_engine::build(const StFile& st) {
     REQUIRE(N == 64, B200RWKV_ERR_UNSUPPORTED, "head_size must be 64");
     REQUIRE(H * N == C, B200RWKV_ERR_UNSUPPORTED, "num_head * head_size must equal num_emb");
     REQUIRE(C % 64 == 0 && C <= 8192, B200RWKV_ERR_UNSUPPORTED, "num_emb must be a multiple of 64 and <= 8192");
-    REQUIRE(H % world == 0 && F % (64 * world) == 0 && V % world == 0, B200RWKV_ERR_UNSUPPORTED,
+    REQUIRE(H % world == 0 && F % (8 * world) == 0 && V % world == 0, B200RWKV_ERR_UNSUPPORTED,
             "heads / hidden / vocab do not shard evenly over the tensor-parallel world");
     Cl = C / world; Hl = H / world; Fl = F / world; Vl = V / world;
     const int ver = info.version;
@@ -571,9 +617,23 @@ void b200rwkv_engine::build(const StFile& st) {
     xx1 = (float*)dalloc(TC * 4); sx1 = (float*)dalloc(TC * 4); xx2 = (float*)dalloc(TC * 4);
     f_r = (float*)dalloc(TCl * 4); f_k = (float*)dalloc(TCl * 4); f_v = (float*)dalloc(TCl * 4); f_g = (float*)dalloc(TCl * 4);
     f_w = (float*)dalloc(TCl * 4); f_a = (float*)dalloc(TCl * 4); f_nu = (float*)dalloc(TCl * 4); f_vfirst = (float*)dalloc(TCl * 4);
-    f_rr = (float*)dalloc(TCl * 4);
-    part_att = (float*)dalloc(TC * 4); part_ffn = (float*)dalloc(TC * 4);
-    d_logits = (float*)dalloc((size_t)maxT * Vl * 4);
+    {
+        auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        off_part_att = 0;
+        off_part_ffn = al(off_part_att + TC * 4 * 8);       // up to 8 split-K slices each
+        off_rr = al(off_part_ffn + TC * 4 * 8);
+        off_logits = al(off_rr + TCl * 4);
+        off_flags = al(off_logits + (size_t)maxT * Vl * 4);
+        comm_bytes = al(off_flags + 256);
+        comm_base = (uint8_t*)dalloc(comm_bytes, true);
+        part_att = (float*)(comm_base + off_part_att);
+        part_ffn = (float*)(comm_base + off_part_ffn);
+        f_rr = (float*)(comm_base + off_rr);
+        d_logits = (float*)(comm_base + off_logits);
+        d_epoch = (unsigned*)dalloc(16, true);
+    }
+    const int S_att = pick_split(Cl, cdiv(C, GEMM_BN)), S_ffn = pick_split(Fl, cdiv(C, GEMM_BN));
+    split_att = S_att; split_ffn = S_ffn;
     d_hidden = (float*)dalloc(TC * 4);
     for (int i = 0; i < 6; ++i) a_x[i] = a16_alloc(C);
     a_out = a16_alloc(Cl);
@@ -595,18 +655,20 @@ void b200rwkv_engine::build(const StFile& st) {
         memset(&p, 0, sizeof(p));
         p.C = C; p.meta = mv; p.kq_tile = C / 32;
     };
-    auto f32_seg = [&](const StTensor& t, int n0, int Nn, int k0, int K, const __half* A, float* out, int ldo, int act,
-                       const float* bias) {
+    auto f32_seg = [&](const StTensor& t, int n0, int Nn, int k0, int K, const A16Buf& ab, float* out, int ldo, int act,
+                       const float* bias, int a_koff = 0, int a_mat = 0) {
         SegDesc d;
         d.t = &t; d.n0 = n0; d.N = Nn; d.k0 = k0; d.K = K;
-        d.proto.A = A; d.proto.out_mode = OUT_F32; d.proto.act = act; d.proto.bias = bias; d.proto.out = out; d.proto.ldo = ldo;
+        d.proto.A = ab.p + (size_t)a_mat * ab.halves_per_matrix + (size_t)(a_koff / 8) * 128; d.proto.a_k8 = ab.kq * 4;
+        d.proto.out_mode = OUT_F32; d.proto.act = act; d.proto.bias = bias; d.proto.out = out; d.proto.ldo = ldo;
         return d;
     };
-    auto a16_seg = [&](const StTensor& t, int n0, int Nn, int k0, int K, const __half* A, const A16Buf& dst, int act,
+    auto a16_seg = [&](const StTensor& t, int n0, int Nn, int k0, int K, const A16Buf& ab, const A16Buf& dst, int act,
                        const float* bias) {
         SegDesc d;
         d.t = &t; d.n0 = n0; d.N = Nn; d.k0 = k0; d.K = K;
-        d.proto.A = A; d.proto.out_mode = OUT_A16; d.proto.act = act; d.proto.bias = bias; d.proto.out = dst.p; d.proto.ldo = dst.kq;
+        d.proto.A = ab.p; d.proto.a_k8 = ab.kq * 4;
+        d.proto.out_mode = OUT_A16; d.proto.act = act; d.proto.bias = bias; d.proto.out = dst.p; d.proto.ldo = dst.kq;
         return d;
     };
 
@@ -624,7 +686,8 @@ void b200rwkv_engine::build(const StFile& st) {
         n1.x_in = (l == 0) ? x_a : x_b;
         n1.x_out = x_a;
         if (l > 0) {
-            n1.n_parts = 1; n1.parts[0] = part_ffn;
+            n1.n_parts = S_ffn;
+            for (int sp = 0; sp < S_ffn; ++sp) n1.parts[sp] = part_ffn + (size_t)sp * TC;
             if (ver != 7) { n1.n_gate = 1; n1.gate_cl = Cl; n1.gates[0] = f_rr; }
             n1.commit_dst = ffn_shift + (size_t)(l - 1) * S * C;
             n1.commit_src = xx2;
@@ -661,7 +724,7 @@ void b200rwkv_engine::build(const StFile& st) {
             // W1: [5*Dm, C]
             {
                 std::vector<SegDesc> sv;
-                SegDesc d = a16_seg(st.get(a + "time_mix_w1"), 0, 5 * Dm, 0, C, a_x[5].p, a_lora[0], ACT_TANH, nullptr);
+                SegDesc d = a16_seg(st.get(a + "time_mix_w1"), 0, 5 * Dm, 0, C, a_x[5], a_lora[0], ACT_TANH, nullptr);
                 d.proto.grp = Dm;
                 d.proto.grp_stride = (int)a_lora[0].halves_per_matrix;
                 sv.push_back(d);
@@ -675,6 +738,7 @@ void b200rwkv_engine::build(const StFile& st) {
                     SegDesc d;
                     d.t = &st.get(a + "time_mix_w2"); d.slice = i; d.n0 = 0; d.N = C; d.k0 = 0; d.K = Dm;
                     d.proto.A = a_lora[0].p + (size_t)i * a_lora[0].halves_per_matrix;
+                    d.proto.a_k8 = a_lora[0].kq * 4;
                     d.proto.out_mode = OUT_LERP_A16; d.proto.act = ACT_NONE;
                     d.proto.out = a_x[i].p; d.proto.ldo = a_x[i].kq;
                     d.proto.aux0 = xx1; d.proto.aux1 = sx1; d.proto.aux2 = vec_f32(st, a + names[i], 0, C); d.proto.ld_aux = C;
@@ -685,17 +749,17 @@ void b200rwkv_engine::build(const StFile& st) {
             // R,K,V,G (column parallel by head) + decay LoRA stage 1 (replicated)
             {
                 std::vector<SegDesc> sv;
-                sv.push_back(f32_seg(Wr, c0, Cl, 0, C, a_x[3].p, f_r, Cl, ACT_NONE, nullptr));
-                sv.push_back(f32_seg(Wk, c0, Cl, 0, C, a_x[1].p, f_k, Cl, ACT_NONE, nullptr));
-                sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[2].p, f_v, Cl, ACT_NONE, nullptr));
-                sv.push_back(f32_seg(st.get(a + "gate.weight"), c0, Cl, 0, C, a_x[4].p, f_g, Cl, ACT_SILU, nullptr));
-                sv.push_back(a16_seg(st.get(a + "time_decay_w1"), 0, Dd, 0, C, a_x[0].p, a_lora[1], ACT_TANH, nullptr));
+                sv.push_back(f32_seg(Wr, c0, Cl, 0, C, a_x[3], f_r, Cl, ACT_NONE, nullptr));
+                sv.push_back(f32_seg(Wk, c0, Cl, 0, C, a_x[1], f_k, Cl, ACT_NONE, nullptr));
+                sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[2], f_v, Cl, ACT_NONE, nullptr));
+                sv.push_back(f32_seg(st.get(a + "gate.weight"), c0, Cl, 0, C, a_x[4], f_g, Cl, ACT_SILU, nullptr));
+                sv.push_back(a16_seg(st.get(a + "time_decay_w1"), 0, Dd, 0, C, a_x[0], a_lora[1], ACT_TANH, nullptr));
                 ly.pre.push_back(make_launch(sv));
             }
             // decay LoRA stage 2: w = exp(-exp(time_decay + Wd2 d))
             {
                 std::vector<SegDesc> sv;
-                sv.push_back(f32_seg(st.get(a + "time_decay_w2"), c0, Cl, 0, Dd, a_lora[1].p, f_w, Cl, ACT_EXPNEGEXP,
+                sv.push_back(f32_seg(st.get(a + "time_decay_w2"), c0, Cl, 0, Dd, a_lora[1], f_w, Cl, ACT_EXPNEGEXP,
                                      vec_f32(st, a + "time_decay", c0, Cl)));
                 ly.wd2_index = (int)ly.pre.size();
                 ly.pre.push_back(make_launch(sv));
@@ -711,10 +775,10 @@ void b200rwkv_engine::build(const StFile& st) {
                 n1.mix_out[i] = a_x[1 + i].p;     // k,v,r,g -> a_x[1..4]
             }
             std::vector<SegDesc> sv;
-            sv.push_back(f32_seg(Wr, c0, Cl, 0, C, a_x[3].p, f_r, Cl, ACT_NONE, nullptr));
-            sv.push_back(f32_seg(Wk, c0, Cl, 0, C, a_x[1].p, f_k, Cl, ACT_NONE, nullptr));
-            sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[2].p, f_v, Cl, ACT_NONE, nullptr));
-            sv.push_back(f32_seg(st.get(a + "gate.weight"), c0, Cl, 0, C, a_x[4].p, f_g, Cl, ACT_SILU, nullptr));
+            sv.push_back(f32_seg(Wr, c0, Cl, 0, C, a_x[3], f_r, Cl, ACT_NONE, nullptr));
+            sv.push_back(f32_seg(Wk, c0, Cl, 0, C, a_x[1], f_k, Cl, ACT_NONE, nullptr));
+            sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[2], f_v, Cl, ACT_NONE, nullptr));
+            sv.push_back(f32_seg(st.get(a + "gate.weight"), c0, Cl, 0, C, a_x[4], f_g, Cl, ACT_SILU, nullptr));
             ly.pre.push_back(make_launch(sv));
             {
                 const StTensor& td = st.get(a + "time_decay");
@@ -745,22 +809,22 @@ void b200rwkv_engine::build(const StFile& st) {
             }
             {
                 std::vector<SegDesc> sv;
-                sv.push_back(f32_seg(Wr, c0, Cl, 0, C, a_x[0].p, f_r, Cl, ACT_NONE, nullptr));
-                sv.push_back(f32_seg(Wk, c0, Cl, 0, C, a_x[2].p, f_k, Cl, ACT_NONE, nullptr));
-                sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[3].p, f_v, Cl, ACT_NONE, nullptr));
-                sv.push_back(a16_seg(st.get(a + "w1"), 0, Dw, 0, C, a_x[1].p, a_lora[0], ACT_TANH, nullptr));
-                sv.push_back(a16_seg(st.get(a + "a1"), 0, Da, 0, C, a_x[4].p, a_lora[1], ACT_NONE, nullptr));
-                if (l > 0) sv.push_back(a16_seg(st.get(a + "v1"), 0, Dv, 0, C, a_x[3].p, a_lora[2], ACT_NONE, nullptr));
-                sv.push_back(a16_seg(st.get(a + "g1"), 0, Dg, 0, C, a_x[5].p, a_lora[3], ACT_SIGMOID, nullptr));
+                sv.push_back(f32_seg(Wr, c0, Cl, 0, C, a_x[0], f_r, Cl, ACT_NONE, nullptr));
+                sv.push_back(f32_seg(Wk, c0, Cl, 0, C, a_x[2], f_k, Cl, ACT_NONE, nullptr));
+                sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[3], f_v, Cl, ACT_NONE, nullptr));
+                sv.push_back(a16_seg(st.get(a + "w1"), 0, Dw, 0, C, a_x[1], a_lora[0], ACT_TANH, nullptr));
+                sv.push_back(a16_seg(st.get(a + "a1"), 0, Da, 0, C, a_x[4], a_lora[1], ACT_NONE, nullptr));
+                if (l > 0) sv.push_back(a16_seg(st.get(a + "v1"), 0, Dv, 0, C, a_x[3], a_lora[2], ACT_NONE, nullptr));
+                sv.push_back(a16_seg(st.get(a + "g1"), 0, Dg, 0, C, a_x[5], a_lora[3], ACT_SIGMOID, nullptr));
                 ly.pre.push_back(make_launch(sv));
             }
             {
                 std::vector<SegDesc> sv;
-                sv.push_back(f32_seg(st.get(a + "w2"), c0, Cl, 0, Dw, a_lora[0].p, f_w, Cl, ACT_V7DECAY, vec_f32(st, a + "w0", c0, Cl)));
-                sv.push_back(f32_seg(st.get(a + "a2"), c0, Cl, 0, Da, a_lora[1].p, f_a, Cl, ACT_SIGMOID, vec_f32(st, a + "a0", c0, Cl)));
+                sv.push_back(f32_seg(st.get(a + "w2"), c0, Cl, 0, Dw, a_lora[0], f_w, Cl, ACT_V7DECAY, vec_f32(st, a + "w0", c0, Cl)));
+                sv.push_back(f32_seg(st.get(a + "a2"), c0, Cl, 0, Da, a_lora[1], f_a, Cl, ACT_SIGMOID, vec_f32(st, a + "a0", c0, Cl)));
                 if (l > 0)
-                    sv.push_back(f32_seg(st.get(a + "v2"), c0, Cl, 0, Dv, a_lora[2].p, f_nu, Cl, ACT_SIGMOID, vec_f32(st, a + "v0", c0, Cl)));
-                sv.push_back(f32_seg(st.get(a + "g2"), c0, Cl, 0, Dg, a_lora[3].p, f_g, Cl, ACT_NONE, nullptr));
+                    sv.push_back(f32_seg(st.get(a + "v2"), c0, Cl, 0, Dv, a_lora[2], f_nu, Cl, ACT_SIGMOID, vec_f32(st, a + "v0", c0, Cl)));
+                sv.push_back(f32_seg(st.get(a + "g2"), c0, Cl, 0, Dg, a_lora[3], f_g, Cl, ACT_NONE, nullptr));
                 ly.pre.push_back(make_launch(sv));
             }
             wk.w = f_w; wk.a = f_a; wk.nu = f_nu; wk.v_first = f_vfirst; wk.layer0 = (l == 0);
@@ -771,16 +835,21 @@ void b200rwkv_engine::build(const StFile& st) {
 
         // ---------------- output projection (row parallel) -> partial ----------------
         {
+            // row-parallel: K is cut into `S_att` static slices, one partial buffer each (summed by the
+            // next LN stage in fixed order); with tiles * S CTAs every CTA owns whole tiles: no fix-up
             std::vector<SegDesc> sv;
-            sv.push_back(f32_seg(Wo, 0, C, c0, Cl, a_out.p, part_att, C, ACT_NONE, nullptr));
-            ly.o = make_launch(sv);
+            for (int sp = 0; sp < S_att; ++sp)
+                sv.push_back(f32_seg(Wo, 0, C, c0 + sp * (Cl / S_att), Cl / S_att, a_out, part_att + (size_t)sp * TC, C, ACT_NONE,
+                                     nullptr, sp * (Cl / S_att)));
+            ly.o = make_launch(sv, S_att > 1 ? cdiv(C, GEMM_BN) * S_att : 0);
         }
 
         // ---------------- LN2 ----------------
         LnMixParams& n2 = ly.ln2;
         base_ln(n2);
         n2.x_in = x_a; n2.x_out = x_b;
-        n2.n_parts = 1; n2.parts[0] = part_att;
+        n2.n_parts = S_att;
+        for (int sp = 0; sp < S_att; ++sp) n2.parts[sp] = part_att + (size_t)sp * TC;
         n2.ln_w = vec_f32(st, b + "ln2.weight", 0, C);
         n2.ln_b = vec_f32(st, b + "ln2.bias", 0, C);
         n2.shift_state = ffn_sh;
@@ -793,7 +862,7 @@ void b200rwkv_engine::build(const StFile& st) {
             n2.mu[0] = vec_f32(st, f + "x_k", 0, C);
             n2.mix_out[0] = a_x[0].p;
             std::vector<SegDesc> sv;
-            sv.push_back(a16_seg(Fk, f0, Fl, 0, C, a_x[0].p, a_kk, ACT_RELU2, nullptr));
+            sv.push_back(a16_seg(Fk, f0, Fl, 0, C, a_x[0], a_kk, ACT_RELU2, nullptr));
             ly.ffn.push_back(make_launch(sv));
         } else {
             n2.n_mix = 2;
@@ -807,21 +876,24 @@ void b200rwkv_engine::build(const StFile& st) {
             n2.mix_out[0] = a_x[0].p;
             n2.mix_out[1] = a_x[1].p;
             std::vector<SegDesc> sv;
-            sv.push_back(a16_seg(Fk, f0, Fl, 0, C, a_x[0].p, a_kk, ACT_RELU2, nullptr));
-            sv.push_back(f32_seg(st.get(f + "receptance.weight"), c0, Cl, 0, C, a_x[1].p, f_rr, Cl, ACT_SIGMOID, nullptr));
+            sv.push_back(a16_seg(Fk, f0, Fl, 0, C, a_x[0], a_kk, ACT_RELU2, nullptr));
+            sv.push_back(f32_seg(st.get(f + "receptance.weight"), c0, Cl, 0, C, a_x[1], f_rr, Cl, ACT_SIGMOID, nullptr));
             ly.ffn.push_back(make_launch(sv));
         }
         {
             std::vector<SegDesc> sv;
-            sv.push_back(f32_seg(Fv, 0, C, f0, Fl, a_kk.p, part_ffn, C, ACT_NONE, nullptr));
-            ly.ffn.push_back(make_launch(sv));
+            for (int sp = 0; sp < S_ffn; ++sp)
+                sv.push_back(f32_seg(Fv, 0, C, f0 + sp * (Fl / S_ffn), Fl / S_ffn, a_kk, part_ffn + (size_t)sp * TC, C, ACT_NONE,
+                                     nullptr, sp * (Fl / S_ffn)));
+            ly.ffn.push_back(make_launch(sv, S_ffn > 1 ? cdiv(C, GEMM_BN) * S_ffn : 0));
         }
     }
 
     // ---------------- ln_out + head ----------------
     memset(&lnout, 0, sizeof(lnout));
     lnout.x_in = x_b; lnout.C = C; lnout.meta = mv;
-    lnout.n_parts = 1; lnout.parts[0] = part_ffn;
+    lnout.n_parts = S_ffn;
+    for (int sp = 0; sp < S_ffn; ++sp) lnout.parts[sp] = part_ffn + (size_t)sp * TC;
     if (ver != 7) { lnout.n_gate = 1; lnout.gate_cl = Cl; lnout.gates[0] = f_rr; }
     lnout.ln_w = vec_f32(st, "ln_out.weight", 0, C);
     lnout.ln_b = vec_f32(st, "ln_out.bias", 0, C);
@@ -831,7 +903,7 @@ void b200rwkv_engine::build(const StFile& st) {
     lnout.hidden_out = d_hidden;
     {
         std::vector<SegDesc> sv;
-        sv.push_back(f32_seg(st.get("head.weight"), v0, Vl, 0, C, a_head.p, d_logits, Vl, ACT_NONE, nullptr));
+        sv.push_back(f32_seg(st.get("head.weight"), v0, Vl, 0, C, a_head, d_logits, Vl, ACT_NONE, nullptr));
         head = make_launch(sv);
         head.p.nrows = d_meta + 2;    // R
     }
@@ -845,40 +917,74 @@ void b200rwkv_engine::build(const StFile& st) {
     head.p.ws = gemm_ws;
 
     build_mega(st);
+    if (world == 1) {
+        peer_base[0] = comm_base;
+        finalize_tp();
+    }
     CK(cudaDeviceSynchronize());
     CK(cudaFree(d_tmp));
     d_tmp = nullptr;
 }
 
 // -----------------------------------------------------------------------------------------
+// Tensor parallel wiring: every LN stage sums the partial projections of ALL ranks (rank-major,
+// then split-K slice: the same fixed order on every rank, so the replicated residual stream stays
+// bit-identical across ranks) straight out of the peers' comm blocks, and takes the channel-mix
+// gate block-wise from the rank that owns those columns.
+// -----------------------------------------------------------------------------------------
+void b200rwkv_engine::finalize_tp() {
+    const size_t TC = (size_t)maxT * C;
+    const int ver = info.version;
+    auto parts_of = [&](size_t off, int S, const float** dst) {
+        int n = 0;
+        for (int q = 0; q < world; ++q)
+            for (int sp = 0; sp < S; ++sp) dst[n++] = (const float*)(peer_base[q] + off) + (size_t)sp * TC;
+        return n;
+    };
+    auto gates_of = [&](const float** dst) {
+        for (int q = 0; q < world; ++q) dst[q] = (const float*)(peer_base[q] + off_rr);
+    };
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = layers[l];
+        if (l > 0) {
+            ly.ln1.n_parts = parts_of(off_part_ffn, split_ffn, ly.ln1.parts);
+            if (ver != 7) { ly.ln1.n_gate = world; ly.ln1.gate_cl = Cl; gates_of(ly.ln1.gates); }
+        }
+        ly.ln2.n_parts = parts_of(off_part_att, split_att, ly.ln2.parts);
+    }
+    lnout.n_parts = parts_of(off_part_ffn, split_ffn, lnout.parts);
+    if (ver != 7) { lnout.n_gate = world; lnout.gate_cl = Cl; gates_of(lnout.gates); }
+    memset(&tpbar, 0, sizeof(tpbar));
+    for (int q = 0; q < world; ++q) tpbar.flags[q] = (unsigned*)(peer_base[q] + off_flags);
+    tpbar.epoch = d_epoch;
+    tpbar.rank = rank;
+    tpbar.world = world;
+    build_mega_program();
+    connected = true;
+}
+
+// -----------------------------------------------------------------------------------------
 // whole-step persistent kernel: device-side phase program over the same parameter blocks
 // -----------------------------------------------------------------------------------------
+// Part 1 (needs the model image): weight-side extras of the whole-step kernel.
 void b200rwkv_engine::build_mega(const StFile& st) {
     mega_ok = false;
+    mega_prepared = false;
     const int ver = info.version;
     const int Dd = info.time_decay_adapter;
     if (!use_mega) return;
     if (ver == 6 && (Dd > MEGA_MAX_DD || Dd % 8 != 0)) return;
     if (C > MEGA_MAX_C) return;
-    std::vector<Phase> phases;
-    std::vector<LnMixParams> lns;
-    std::vector<GemmLaunchDev> gemms;
-    std::vector<WkvParams> wkvs;
-    auto add_gemm = [&](const GemmLaunch& g) {
-        GemmLaunchDev d;
-        memset(&d, 0, sizeof(d));
-        d.p = g.p;
-        d.ncta = g.grid;
-        phases.push_back({PH_GEMM, (int)gemms.size()});
-        gemms.push_back(d);
+    mega_lora_cc = (ver == 6) && !getenv("B200RWKV_LORA_GEMM") && info.time_mix_adapter % 8 == 0 &&
+                   5 * info.time_mix_adapter <= num_sms * LORA_MAX_ROWS_PER_CTA;
+    auto upload_raw = [&](const StTensor& t) {
+        __half* d = (__half*)dalloc(t.nbytes, false);
+        CK(cudaMemcpy(d, t.data, t.nbytes, cudaMemcpyHostToDevice));
+        return d;
     };
-    phases.push_back({PH_EMBED, 0});
+    mega_wkvs.clear(); mega_smallns.clear(); mega_smallks.clear();
     for (int l = 0; l < L; ++l) {
         Layer& ly = layers[l];
-        phases.push_back({PH_LN, (int)lns.size()});
-        lns.push_back(ly.ln1);
-        for (int i = 0; i < (int)ly.pre.size(); ++i)
-            if (i != ly.wd2_index) add_gemm(ly.pre[i]);
         WkvParams w = ly.wkv;
         if (ver == 6) {
             // k-major copy of this rank's time_decay_w2 rows, one contiguous [Dd][64] slice per head
@@ -898,15 +1004,74 @@ void b200rwkv_engine::build_mega(const StFile& st) {
             w.d1_kq = a_lora[1].kq;
             w.Dd = Dd;
         }
-        phases.push_back({PH_WKV, (int)wkvs.size()});
-        wkvs.push_back(w);
+        mega_wkvs.push_back(w);
+        if (mega_lora_cc) {
+            // ddlerp LoRA on CUDA cores: no cross-CTA reduction (lora.cuh)
+            const int Dm = info.time_mix_adapter;
+            SmallNParams sn;
+            memset(&sn, 0, sizeof(sn));
+            sn.W = upload_raw(st.get("blocks." + std::to_string(l) + ".att.time_mix_w1"));
+            sn.N = 5 * Dm; sn.K = C;
+            sn.A = a_x[5].p; sn.a_kq = a_x[5].kq;
+            sn.out = a_lora[0].p; sn.grp = Dm; sn.grp_stride = (int)a_lora[0].halves_per_matrix; sn.out_kq = a_lora[0].kq;
+            sn.act = ACT_TANH; sn.nrows = d_meta;
+            mega_smallns.push_back(sn);
+            const __half* w2 = upload_raw(st.get("blocks." + std::to_string(l) + ".att.time_mix_w2"));
+            SmallKParams sk;
+            memset(&sk, 0, sizeof(sk));
+            sk.nseg = 5; sk.nrows = d_meta;
+            for (int j = 0; j < 5; ++j) {
+                const GemmSeg& gs_ = ly.pre[1].p.seg[j];
+                SmallKSeg& q = sk.seg[j];
+                q.W = w2 + (size_t)j * C * Dm; q.N = C; q.K = Dm;
+                q.A = a_lora[0].p + (size_t)j * a_lora[0].halves_per_matrix; q.a_kq = a_lora[0].kq;
+                q.out_mode = OUT_LERP_A16; q.act = ACT_NONE; q.bias = nullptr;
+                q.out = gs_.out; q.ldo = gs_.ldo; q.aux0 = gs_.aux0; q.aux1 = gs_.aux1; q.aux2 = gs_.aux2; q.ld_aux = gs_.ld_aux;
+            }
+            mega_smallks.push_back(sk);
+        }
+    }
+    mega_prepared = true;
+}
+
+// Part 2 (after the tensor-parallel wiring): the device-side phase program.
+void b200rwkv_engine::build_mega_program() {
+    mega_ok = false;
+    if (!mega_prepared) return;
+    const int ver = info.version;
+    std::vector<Phase> phases;
+    std::vector<LnMixParams> lns;
+    std::vector<GemmLaunchDev> gemms;
+    auto add_gemm = [&](const GemmLaunch& g) {
+        GemmLaunchDev d;
+        memset(&d, 0, sizeof(d));
+        d.p = g.p;
+        d.ncta = g.grid;
+        phases.push_back({PH_GEMM, (int)gemms.size()});
+        gemms.push_back(d);
+    };
+    phases.push_back({PH_EMBED, 0});
+    for (int l = 0; l < L; ++l) {
+        Layer& ly = layers[l];
+        phases.push_back({PH_LN, (int)lns.size()});
+        lns.push_back(ly.ln1);
+        for (int i = 0; i < (int)ly.pre.size(); ++i) {
+            if (i == ly.wd2_index) continue;
+            if (mega_lora_cc && i == 0) { phases.push_back({PH_SMALLN, l}); continue; }
+            if (mega_lora_cc && i == 1) { phases.push_back({PH_SMALLK, l}); continue; }
+            add_gemm(ly.pre[i]);
+        }
+        phases.push_back({PH_WKV, l});
         add_gemm(ly.o);
+        if (world > 1) phases.push_back({PH_TPBAR, 0});
         phases.push_back({PH_LN, (int)lns.size()});
         lns.push_back(ly.ln2);
         for (auto& g : ly.ffn) add_gemm(g);
+        if (world > 1) phases.push_back({PH_TPBAR, 0});
     }
     phases.push_back({PH_LNOUT, 0});
     add_gemm(head);
+    if (world > 1) phases.push_back({PH_TPBAR, 0});     // logits shards complete on every rank
 
     auto up = [&](const void* src, size_t bytes) {
         void* d = dalloc(bytes, false);
@@ -920,11 +1085,14 @@ void b200rwkv_engine::build_mega(const StFile& st) {
     mega.embed = (const EmbedParams*)up(&embed, sizeof(embed));
     mega.ln = (const LnMixParams*)up(lns.data(), lns.size() * sizeof(LnMixParams));
     mega.gemm = (const GemmLaunchDev*)up(gemms.data(), gemms.size() * sizeof(GemmLaunchDev));
-    mega.wkv = (const WkvParams*)up(wkvs.data(), wkvs.size() * sizeof(WkvParams));
+    mega.wkv = (const WkvParams*)up(mega_wkvs.data(), mega_wkvs.size() * sizeof(WkvParams));
     mega.lnout = (const LnOutParams*)up(&lnout, sizeof(lnout));
+    if (!mega_smallns.empty()) mega.smalln = (const SmallNParams*)up(mega_smallns.data(), mega_smallns.size() * sizeof(SmallNParams));
+    if (!mega_smallks.empty()) mega.smallk = (const SmallKParams*)up(mega_smallks.data(), mega_smallks.size() * sizeof(SmallKParams));
+    mega.tp = tpbar;
     mega.gbar = (unsigned*)dalloc(16, true);
     mega.meta = MetaView{d_meta, maxT, S};
-    if (getenv("B200RWKV_TRACE")) mega.trace = (unsigned long long*)dalloc((size_t)4 * phases.size() * 4 * 8, true);
+    if (getenv("B200RWKV_TRACE")) mega.trace = (unsigned long long*)dalloc((size_t)4 * phases.size() * 12 * 8, true);
     mega_phase_types.clear();
     for (auto& ph : phases) mega_phase_types.push_back(ph.type);
     void (*kern)(MegaParams) = (ver == 6) ? mega_step_kernel<6> : (ver == 7 ? mega_step_kernel<7> : mega_step_kernel<5>);
@@ -963,11 +1131,11 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
         if (big(g) ? (sk & 8) : (sk & 2)) return;
         launch_gemm(g, MT, s, prof);
     };
-    if (!(sk & 1)) launch_k(embed_ln0_kernel, dim3(rows), dim3(LN_THREADS), (size_t)C * 4, embed, KC_LN, s, prof);
+    if (!(sk & 1)) launch_k(embed_ln0_kernel, dim3(rows), dim3(LN_THREADS), 0, embed, KC_LN, s, prof);
     const int wkv_slots = std::min(S, rows);
     for (int l = 0; l < L; ++l) {
         Layer& ly = layers[l];
-        if (!(sk & 1)) launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), (size_t)C * 4, ly.ln1, KC_LN, s, prof);
+        if (!(sk & 1)) launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, ly.ln1, KC_LN, s, prof);
         for (auto& g : ly.pre) gemm(g);
         if (!(sk & 4)) switch (info.version) {
             case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof); break;
@@ -975,11 +1143,14 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             default: launch_k(wkv_kernel<7>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof); break;
         }
         gemm(ly.o);
-        if (!(sk & 1)) launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), (size_t)C * 4, ly.ln2, KC_LN, s, prof);
+        if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
+        if (!(sk & 1)) launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, ly.ln2, KC_LN, s, prof);
         for (auto& g : ly.ffn) gemm(g);
+        if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
     }
-    if (!(sk & 1)) launch_k(ln_out_kernel, dim3(rows), dim3(LN_THREADS), (size_t)C * 4, lnout, KC_LN, s, prof);
+    if (!(sk & 1)) launch_k(ln_out_kernel, dim3(rows), dim3(LN_THREADS), 0, lnout, KC_LN, s, prof);
     if (MTR > 0 && !(sk & 16)) launch_gemm(head, MTR, s, prof);
+    if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
 }
 
 static inline int mt_bucket(int rows) { return rows <= 16 ? 1 : (rows <= 32 ? 2 : 4); }
@@ -1070,6 +1241,7 @@ int b200rwkv_engine::fill_meta(int* m, const std::vector<int>& slots, const std:
 void b200rwkv_engine::infer(int nslot, const int32_t* slot, const int32_t* ntok, const uint32_t* tokens, const int32_t* option,
                             float* logits_out, size_t cap, int32_t* rows_out) {
     REQUIRE(nslot >= 0 && (nslot == 0 || (slot && ntok && option)), B200RWKV_ERR_INVALID, "infer: null argument");
+    REQUIRE(connected, B200RWKV_ERR_INVALID, "tensor-parallel engine is not connected (b200rwkv_tp_connect)");
     std::vector<char> seen(S, 0);
     size_t total_rows = 0, total_tok = 0;
     for (int i = 0; i < nslot; ++i) {
@@ -1084,8 +1256,9 @@ void b200rwkv_engine::infer(int nslot, const int32_t* slot, const int32_t* ntok,
         total_tok += (size_t)ntok[i];
     }
     REQUIRE(total_tok == 0 || tokens, B200RWKV_ERR_INVALID, "infer: null tokens");
-    REQUIRE(total_rows * (size_t)V <= cap || total_rows == 0, B200RWKV_ERR_INVALID, "infer: logits buffer too small");
-    REQUIRE(total_rows == 0 || logits_out, B200RWKV_ERR_INVALID, "infer: null logits buffer");
+    const bool want_logits = (rank == 0);          // tensor parallel: rank 0 gathers all vocabulary shards
+    REQUIRE(!want_logits || total_rows * (size_t)V <= cap || total_rows == 0, B200RWKV_ERR_INVALID, "infer: logits buffer too small");
+    REQUIRE(!want_logits || total_rows == 0 || logits_out, B200RWKV_ERR_INVALID, "infer: null logits buffer");
     const int step_cap = std::min(chunk, maxT);
     // cursor over entries
     std::vector<size_t> base(nslot + 1, 0);
@@ -1116,9 +1289,15 @@ void b200rwkv_engine::infer(int nslot, const int32_t* slot, const int32_t* ntok,
         last_T = T;
         CK(cudaMemcpyAsync(d_meta, h_meta, meta_ints * 4, cudaMemcpyHostToDevice, stream));
         run_step(mt_bucket(T), R > 0 ? mt_bucket(R) : 0);
-        if (R > 0) {
-            CK(cudaMemcpyAsync(out, d_logits, (size_t)R * Vl * 4, cudaMemcpyDeviceToHost, stream));
-            out += (size_t)R * Vl;
+        if (R > 0 && want_logits) {
+            if (world == 1) {
+                CK(cudaMemcpyAsync(out, d_logits, (size_t)R * V * 4, cudaMemcpyDeviceToHost, stream));
+            } else {
+                for (int q = 0; q < world; ++q)      // column block q of every row, straight from rank q's shard
+                    CK(cudaMemcpy2DAsync(out + (size_t)q * Vl, (size_t)V * 4, peer_base[q] + off_logits, (size_t)Vl * 4,
+                                         (size_t)Vl * 4, R, cudaMemcpyDeviceToHost, stream));
+            }
+            out += (size_t)R * V;
         }
         CK(cudaStreamSynchronize(stream));
     }
@@ -1180,6 +1359,12 @@ int32_t b200rwkv_create_tp(const uint8_t* st, size_t len, int32_t device, int32_
             std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(ce));
     REQUIRE(device >= 0 && device < ndev, B200RWKV_ERR_INVALID, "device ordinal out of range");
     CK(cudaSetDevice(device));
+    watchdog_setup();
+    if (g_wd_host) {
+        unsigned* dptr = nullptr;
+        CK(cudaHostGetDevicePointer(&dptr, g_wd_host, 0));
+        CK(cudaMemcpyToSymbol(g_watchdog, &dptr, sizeof(dptr)));
+    }
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     REQUIRE(prop.major == 10, B200RWKV_ERR_UNSUPPORTED,
@@ -1202,17 +1387,77 @@ int32_t b200rwkv_create(const uint8_t* st, size_t len, int32_t device, int32_t m
     return b200rwkv_create_tp(st, len, device, max_batch, token_chunk_size, precision, 0, 1, out);
 }
 
+struct TpHandle {            // wire format of the 128-byte blob
+    cudaIpcMemHandle_t ipc;  // 64 bytes
+    int32_t rank, world;
+    uint64_t comm_bytes;
+    int32_t pid;
+    int32_t device;
+};
+static_assert(sizeof(TpHandle) <= B200RWKV_TP_HANDLE_BYTES, "handle blob too large");
+
 int32_t b200rwkv_tp_export(b200rwkv_engine* e, uint8_t* handle_out) {
     API_BEGIN(e)
     REQUIRE(e && handle_out, B200RWKV_ERR_INVALID, "null argument");
-    throw Error(B200RWKV_ERR_UNSUPPORTED, "tensor-parallel exchange is not implemented yet");
+    CK(cudaSetDevice(e->dev));
+    TpHandle h;
+    memset(&h, 0, sizeof(h));
+    CK(cudaIpcGetMemHandle(&h.ipc, e->comm_base));
+    h.rank = e->rank; h.world = e->world; h.comm_bytes = e->comm_bytes; h.pid = (int32_t)getpid(); h.device = e->dev;
+    memset(handle_out, 0, B200RWKV_TP_HANDLE_BYTES);
+    memcpy(handle_out, &h, sizeof(h));
     API_END
 }
 
 int32_t b200rwkv_tp_connect(b200rwkv_engine* e, const uint8_t* handles) {
     API_BEGIN(e)
     REQUIRE(e && handles, B200RWKV_ERR_INVALID, "null argument");
-    throw Error(B200RWKV_ERR_UNSUPPORTED, "tensor-parallel exchange is not implemented yet");
+    REQUIRE(!e->connected || e->world == 1, B200RWKV_ERR_INVALID, "already connected");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->dev));
+    for (int q = 0; q < e->world; ++q) {
+        TpHandle h;
+        memcpy(&h, handles + (size_t)q * B200RWKV_TP_HANDLE_BYTES, sizeof(h));
+        REQUIRE(h.rank == q && h.world == e->world && h.comm_bytes == e->comm_bytes, B200RWKV_ERR_INVALID,
+                "tp_connect: handle blobs are not rank-ordered or come from a different model/world");
+        if (q == e->rank) {
+            e->peer_base[q] = e->comm_base;
+        } else {
+            void* p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+            e->peer_base[q] = (uint8_t*)p;
+        }
+    }
+    e->finalize_tp();
+    CK(cudaDeviceSynchronize());
+    API_END
+}
+
+// In-process variant (all ranks live in this process, e.g. tests with several ranks on one GPU, or a
+// host that owns every GPU of the box as in SURVEY.md §8b): exchange the comm-block pointers directly.
+int32_t b200rwkv_tp_connect_local(b200rwkv_engine** engines, int32_t n) {
+    API_BEGIN((b200rwkv_engine*)nullptr)
+    REQUIRE(engines && n >= 1 && n <= 8, B200RWKV_ERR_INVALID, "bad argument");
+    for (int i = 0; i < n; ++i)
+        REQUIRE(engines[i] && engines[i]->world == n && engines[i]->rank == i && engines[i]->comm_bytes == engines[0]->comm_bytes,
+                B200RWKV_ERR_INVALID, "tp_connect_local: engines must be rank-ordered ranks of one world");
+    for (int i = 0; i < n; ++i) {
+        b200rwkv_engine* e = engines[i];
+        CK(cudaSetDevice(e->dev));
+        for (int q = 0; q < n; ++q) {
+            if (engines[q]->dev != e->dev) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, e->dev, engines[q]->dev));
+                REQUIRE(can, B200RWKV_ERR_CUDA, "no peer access between the devices");
+                cudaError_t pe = cudaDeviceEnablePeerAccess(engines[q]->dev, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+                (void)cudaGetLastError();
+            }
+            e->peer_base[q] = engines[q]->comm_base;
+        }
+        e->finalize_tp();
+        CK(cudaDeviceSynchronize());
+    }
     API_END
 }
 
@@ -1490,6 +1735,12 @@ int32_t b200rwkv_debug_read(b200rwkv_engine* e, const char* name, float* out, si
             if (n == f.n) {
                 REQUIRE((size_t)T * f.cols <= cap, B200RWKV_ERR_INVALID, "debug buffer too small");
                 CK(cudaMemcpy(out, f.p, (size_t)T * f.cols * 4, cudaMemcpyDeviceToHost));
+                const int nsum = (n == "part_att") ? e->split_att : (n == "part_ffn" ? e->split_ffn : 1);
+                std::vector<float> tmp((size_t)T * f.cols);
+                for (int sp = 1; sp < nsum; ++sp) {       // split-K partials: sum the slices
+                    CK(cudaMemcpy(tmp.data(), f.p + (size_t)sp * e->maxT * e->C, tmp.size() * 4, cudaMemcpyDeviceToHost));
+                    for (size_t i = 0; i < tmp.size(); ++i) out[i] += tmp[i];
+                }
                 return f.cols;
             }
         struct A { std::string n; const A16Buf* b; int cols; int mat; };
@@ -1521,7 +1772,7 @@ int32_t b200rwkv_debug_read(b200rwkv_engine* e, const char* name, float* out, si
 int32_t b200rwkv_debug_trace(b200rwkv_engine* e, uint64_t* out, size_t cap, int32_t* types, int32_t* nphase) {
     if (!e || !out || !types || !nphase) return B200RWKV_ERR_INVALID;
     if (!e->mega_ok || !e->mega.trace) { e->err = "no trace (set B200RWKV_TRACE=1)"; return B200RWKV_ERR_INVALID; }
-    const size_t n = (size_t)4 * e->mega.nphase * 4;
+    const size_t n = (size_t)4 * e->mega.nphase * 12;
     if (cap < n) return B200RWKV_ERR_INVALID;
     cudaSetDevice(e->dev);
     cudaStreamSynchronize(e->stream);

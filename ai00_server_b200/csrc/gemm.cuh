@@ -11,12 +11,13 @@
 // cycles per sub-partition; profiles/r01_gemm_mma_sync.md), so the tensor work is on tcgen05:
 //   * swap-AB: the WEIGHT tile is the 128-row M operand, the token tile is the N=16 operand, the
 //     f32 accumulator (128 lanes x 16 columns) lives in TMEM; one elected thread issues
-//     tcgen05.mma.cta_group::1.kind::f16, four k16 steps per 16 KB stage;
-//   * weights are re-tiled ONCE at load into 16 KB stage blocks (128 output rows x 64 k) already
+//     tcgen05.mma.cta_group::1.kind::f16, eight k16 steps per 32 KB stage;
+//   * weights are re-tiled ONCE at load into 32 KB stage blocks (128 output rows x 128 k) already
 //     in the UMMA canonical K-major / no-swizzle shared-memory layout, so a pipeline stage is ONE
 //     contiguous 1-D bulk TMA copy (cp.async.bulk -> UBLKCP) that the tensor core reads in place;
-//     activations use the matching A16 layout (common.cuh): one 2 KB bulk copy per stage;
-//   * warp roles: one TMA producer lane drives a 9-12 stage mbarrier ring; one MMA lane consumes
+//     activations use the matching A16 layout (common.cuh): one 4 KB bulk copy per stage (the
+//     issue rate of bulk copies, ~0.3 us each per thread, is what sizes the stage);
+//   * warp roles: one TMA producer lane drives a 4-6 stage mbarrier ring; one MMA lane consumes
 //     it (tcgen05.commit releases each slot when its MMAs retire); four epilogue warps drain the
 //     double-buffered TMEM accumulator with tcgen05.ld while the next tile's MMAs run;
 //   * work is split stream-K style: the launch's stage blocks (all segments, all tiles) form one
@@ -33,18 +34,19 @@
 namespace b200 {
 
 constexpr int GEMM_BN = 128;                 // output rows (weight rows) per tile = UMMA M
-constexpr int GEMM_BK = 64;                  // k per stage block (4 x UMMA K=16)
-constexpr int GEMM_WBYTES = GEMM_BN * GEMM_BK * 2;   // 16 KB
-constexpr int GEMM_ABYTES = 16 * GEMM_BK * 2;        // 2 KB per 16-token tile
+constexpr int GEMM_BK = 128;                 // k per stage block (8 x UMMA K=16)
+constexpr int GEMM_WBYTES = GEMM_BN * GEMM_BK * 2;   // 32 KB
+constexpr int GEMM_ABYTES = 16 * GEMM_BK * 2;        // 4 KB per 16-token tile
+constexpr int GEMM_K8 = GEMM_BK / 8;                 // 16-byte k chunks per stage
 constexpr int GEMM_EPI_WARPS = 4;            // one per TMEM lane quarter
 constexpr int GEMM_EPI_THREADS = GEMM_EPI_WARPS * 32;
 constexpr int GEMM_THREADS = (GEMM_EPI_WARPS + 2) * 32;   // + MMA warp + TMA producer warp
 constexpr int GEMM_MAX_SEG = 8;
 constexpr int GEMM_SMEM_BUDGET = 221184;     // 216 KB for stages
 // canonical K-major no-swizzle strides of the two operands in shared memory
-constexpr uint32_t GEMM_W_LBO = 16 * 128;    // weight stage [k8 chunk 8][row group 16][8 rows][16 B]
+constexpr uint32_t GEMM_W_LBO = 16 * 128;    // weight stage [k8 chunk 16][row group 16][8 rows][16 B]
 constexpr uint32_t GEMM_W_SBO = 128;
-constexpr uint32_t GEMM_A_LBO = 2 * 128;     // token tile   [k8 chunk 8][row group 2][8 rows][16 B]
+constexpr uint32_t GEMM_A_LBO = 2 * 128;     // token tile   [k8 chunk 16][row group 2][8 rows][16 B]
 constexpr uint32_t GEMM_A_SBO = 128;
 
 enum OutMode : int {
@@ -54,8 +56,9 @@ enum OutMode : int {
 };
 
 struct GemmSeg {
-    const __half* A;      // A16 activations for this segment
-    int KB;               // 64-wide k blocks (K padded up)
+    const __half* A;      // A16 activations for this segment (already offset to the segment's first k)
+    int a_k8;             // 16-byte k chunks per 16-token tile of the A16 buffer (its padded K / 8)
+    int KB;               // 128-wide k blocks (K padded up)
     int tiles;            // 128-row output tiles (N padded up)
     int N;                // valid output columns
     int blk_begin;        // first linear stage block of this segment
@@ -154,11 +157,11 @@ __device__ __forceinline__ void gemm_mma_role(const GemmParams& p, const int b0,
     while (!w.done()) {
         const int nblk = w.nblk();
         const unsigned acc = segcount & 1u, use = segcount >> 1;
-        if (use > 0) mbar_wait(tempty_bar + acc * 8, (use - 1) & 1u);     // epilogue drained this buffer
+        if (use > 0) mbar_wait(tempty_bar + acc * 8, (use - 1) & 1u, 11);     // epilogue drained this buffer
         tc_fence_after();
         const uint32_t d0 = tmem_base + acc * (16 * MT);
         for (int i = 0; i < nblk; ++i) {
-            mbar_wait(full_bar + rp.stage * 8, rp.phase);
+            mbar_wait(full_bar + rp.stage * 8, rp.phase, 12);
             tc_fence_after();
             const uint32_t st = smem_base + rp.stage * STAGE_BYTES;
 #pragma unroll
@@ -202,7 +205,7 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
     while (!w.done()) {
         const GemmSeg& sg = p.seg[w.seg];
         const unsigned acc = segcount & 1u, use = segcount >> 1;
-        mbar_wait(tfull_bar + acc * 8, use & 1u);
+        mbar_wait(tfull_bar + acc * 8, use & 1u, 13);
         stamp(8);
         tc_fence_after();
         float v[MT][16];
@@ -380,15 +383,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
                 const uint32_t st = smem_base + stage * Cfg::STAGE_BYTES;
                 const uint32_t fb = full_bar + stage * 8;
                 if (it >= Cfg::NSTAGE) {
-                    mbar_wait(empty_bar + stage * 8, ephase);
+                    mbar_wait(empty_bar + stage * 8, ephase, 14);
                     mbar_expect_tx(fb, Cfg::STAGE_BYTES);
                     bulk_g2s_hint(st, p.W + (size_t)b * GEMM_WBYTES, GEMM_WBYTES, fb, pol_w);
                 }
-                const int k8_tile = sg->KB * 8;       // 16-byte k chunks per token tile
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt)
                     bulk_g2s_hint(st + GEMM_WBYTES + mt * GEMM_ABYTES,
-                                  sg->A + ((size_t)mt * k8_tile + 8 * kb) * 128, GEMM_ABYTES, fb, pol_a);
+                                  sg->A + ((size_t)mt * sg->a_k8 + GEMM_K8 * kb) * 128, GEMM_ABYTES, fb, pol_a);
                 if (++stage == Cfg::NSTAGE) { stage = 0; ephase ^= 1; }
                 if (++kb == sg->KB) kb = 0;
                 if (--blocks_left_in_seg == 0 && b + 1 < b1) {
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 
 // ---------------------------------------------------------------------------------------
 // One-time weight re-tiling:  W[N, K] row-major f16  ->  stage blocks in the UMMA canonical
-// K-major / no-swizzle layout:  block(tile, kb) = [k8 chunk 8][row group 16][row 8][8 halves], zero padded.
+// K-major / no-swizzle layout:  block(tile, kb) = [k8 chunk 16][row group 16][row 8][8 halves], zero padded.
 // Supports a row-parallel / column-parallel shard: source sub-matrix rows [n0, n0+N), cols [k0, k0+K)
 // of a matrix with row stride ld.
 // ---------------------------------------------------------------------------------------
@@ -437,7 +439,7 @@ __global__ void repack_weight_kernel(const __half* __restrict__ src, int ld, int
         size_t r = i;
         const int row = r % 8; r /= 8;       // row inside the 8-row core matrix
         const int mi = r % 16; r /= 16;      // row group
-        const int kj = r % 8; r /= 8;        // 8-half (16-byte) k chunk
+        const int kj = r % GEMM_K8; r /= GEMM_K8;   // 8-half (16-byte) k chunk
         const int kb = r % KB; r /= KB;
         const int tile = (int)r;
         const int n = tile * GEMM_BN + mi * 8 + row;

@@ -68,6 +68,49 @@ __global__ void state_xform_kernel(const StateXform p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Tensor-parallel rendezvous: one flag word per (reader rank, writer rank) in the reader's comm
+// block, written over NVLink peer memory.  The row-parallel projections leave their partial sums
+// in the local comm block; after this barrier every rank's LN stage reads all ranks' partials
+// straight from peer memory (one-shot all-reduce fused into the consumer, fixed rank order).
+// The epoch lives in device memory so a captured graph replays correctly.
+// ---------------------------------------------------------------------------------------
+struct TpBar {
+    unsigned* flags[8];     // flags[q]: rank q's flag array [8] (peer-mapped for q != rank)
+    unsigned* epoch;        // local
+    int rank, world;
+};
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// threads 0..world-1 of one warp; all prior writes of the calling grid/CTA must already be ordered
+// before the call (kernel boundary, or grid barrier + fence)
+__device__ __forceinline__ void tp_barrier(const TpBar& b, const int lane) {
+    unsigned e = 0;
+    if (lane == 0) {
+        e = *b.epoch + 1;
+        *b.epoch = e;
+    }
+    e = __shfl_sync(0xffffffffu, e, 0);
+    if (lane < b.world) {
+        __threadfence_system();
+        st_release_sys(b.flags[lane] + b.rank, e);
+        SpinGuard sg_;
+        while (ld_acquire_sys(b.flags[b.rank] + lane) < e) sg_.poll(5u, (unsigned)lane, e, (unsigned)b.rank);
+    }
+    __syncwarp();
+    __threadfence_system();
+}
+__global__ void tp_barrier_kernel(const TpBar b) {
+    pdl_wait();
+    tp_barrier(b, threadIdx.x);
+}
+
 __global__ void f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n, float scale, float bias) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = __half2float(src[i]) * scale + bias;

@@ -12,9 +12,9 @@
 // The shift state of the PREVIOUS LN stage is committed here (dst <- last token's xx), which
 // keeps every state write strictly after all reads of the old value with no extra launch.
 //
-// Code shape: these rows run once per launch / per phase of the whole-step kernel, i.e. with a
-// cold instruction cache (measured: straight-line unrolled code costs microseconds of
-// instruction fetch), so every pass is a small rolled loop over a shared-memory copy of the row.
+// Code shape: only a handful of CTAs run these rows and everything they touch sits at L2 latency
+// (~0.5 us per dependent round trip), so the row lives in registers and every batch of loads is
+// issued together; parameters that do not depend on the phase are requested before the reductions.
 #pragma once
 #include "common.cuh"
 
@@ -48,6 +48,7 @@ struct LnMixParams {
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
 // residual source shared by the LN stages: x_in + gate (.) sum_p parts[p]
 struct ResidualSrc {     // held by value: pointers into kernel-parameter space would turn into slow generic loads
@@ -65,46 +66,64 @@ __device__ __forceinline__ ResidualSrc make_residual_src(const P& p) {
     return r;
 }
 
-// updated residual at (t, c..c+3)
-__device__ __noinline__ float4 residual4(const ResidualSrc& r, const int t, const int c) {
-    float4 a = ld4(r.x_in + (size_t)t * r.C + c);
-    if (r.n_parts > 0) {
-        float4 s = ld4(r.parts[0] + (size_t)t * r.C + c);
-#pragma unroll 1
-        for (int q = 1; q < r.n_parts; ++q) {      // fixed rank order: deterministic, identical on all ranks
-            const float4 b = ld4(r.parts[q] + (size_t)t * r.C + c);
-            s.x += b.x; s.y += b.y; s.z += b.z; s.w += b.w;
-        }
-        if (r.n_gate > 0) {
+// Row t of the updated residual into a[NV] (thread owns columns 4*(tid + 256 j)).  Memory-level
+// parallelism is what matters here (a handful of CTAs, everything L2-latency bound): all loads of
+// a batch (x + 4 partials, then 4 more partials + gate) are in flight together.
+template <int NV>
+__device__ __forceinline__ void residual_row(const ResidualSrc& r, const int t, float4 (&a)[NV]) {
+    const int C = r.C;
+    const size_t base = (size_t)t * C;
+    float4 s[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = 4 * (threadIdx.x + LN_THREADS * j);
+        a[j] = (c < C) ? ld4(r.x_in + base + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (r.n_parts == 0) return;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (half * 4 >= r.n_parts) break;
+        float4 v[4][NV];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const int c = 4 * (threadIdx.x + LN_THREADS * j);
+                v[q][j] = (half * 4 + q < r.n_parts && c < C) ? ld4(r.parts[half * 4 + q] + base + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)        // fixed order: deterministic, identical on all ranks
+#pragma unroll
+            for (int j = 0; j < NV; ++j) add4(s[j], v[q][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = 4 * (threadIdx.x + LN_THREADS * j);
+        if (r.n_gate > 0 && c < C) {
             const int gb = c / r.gate_cl;
             const float4 gt = ld4(r.gates[gb] + (size_t)t * r.gate_cl + (c - gb * r.gate_cl));
-            s.x *= gt.x; s.y *= gt.y; s.z *= gt.z; s.w *= gt.w;
+            s[j].x *= gt.x; s[j].y *= gt.y; s[j].z *= gt.z; s[j].w *= gt.w;
         }
-        a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+        add4(a[j], s[j]);
     }
-    return a;
 }
 
-// mean / rstd of row t of the updated residual; optionally keeps the row in `row` and writes x_out
-template <bool MEGA>
-__device__ __forceinline__ void ln_stats(const ResidualSrc& r, const int t, float* row, float* x_out, float* red, float& mean,
-                                         float& rstd) {
-    const int C = r.C;
+// two-pass mean / rstd of a row held in registers
+template <int NV, bool MEGA>
+__device__ __forceinline__ void row_stats(const int C, const float4 (&a)[NV], float* red, float& mean, float& rstd) {
     float s = 0.f;
-#pragma unroll 1
-    for (int c = 4 * threadIdx.x; c < C; c += 4 * LN_THREADS) {
-        const float4 a = residual4(r, t, c);
-        if (row) *reinterpret_cast<float4*>(row + c) = a;
-        if (x_out) *reinterpret_cast<float4*>(x_out + (size_t)t * C + c) = a;
-        s += (a.x + a.y) + (a.z + a.w);
-    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += (a[j].x + a[j].y) + (a[j].z + a[j].w);
     mean = block_sum<MEGA>(s, red) / (float)C;
     float s2 = 0.f;
-#pragma unroll 1
-    for (int c = 4 * threadIdx.x; c < C; c += 4 * LN_THREADS) {
-        const float4 a = row ? *reinterpret_cast<const float4*>(row + c) : residual4(r, t, c);
-        const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
-        s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = 4 * (threadIdx.x + LN_THREADS * j);
+        if (c < C) {
+            const float dx = a[j].x - mean, dy = a[j].y - mean, dz = a[j].z - mean, dw = a[j].w - mean;
+            s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
     }
     const float var = block_sum<MEGA>(s2, red) / (float)C;
     rstd = 1.0f / sqrtf(var + LN_EPS);
@@ -119,48 +138,101 @@ __device__ __forceinline__ float4 ln_apply(const float4 a, const float mean, con
     return o;
 }
 
-// `row`: shared-memory buffer of >= C floats
-template <bool MEGA>
-__device__ __forceinline__ void ln_mix_row(const LnMixParams& p, const int t, float* row, float* red) {
+template <int NV, bool MEGA>
+__device__ __forceinline__ void ln_mix_row_nv(const LnMixParams& p, const int t, float* red, unsigned long long* stamps = nullptr) {
+    auto stamp = [&](int i) { if (stamps && threadIdx.x == 0) stamps[i] = globaltimer_ns(); };
+    stamp(0);
     const int C = p.C;
     const int slot = p.meta.tok_slot()[t];
     const int prev_t = p.meta.tok_prev()[t];
     const bool last = p.meta.tok_last()[t] != 0;
     const ResidualSrc r = make_residual_src(p);
-    float mean, rstd, pmean = 0.f, prstd = 0.f;
-    ln_stats<MEGA>(r, t, row, (p.x_out != p.x_in || p.n_parts > 0) ? p.x_out : nullptr, red, mean, rstd);
-    if (prev_t >= 0) ln_stats<MEGA>(r, prev_t, nullptr, nullptr, red, pmean, prstd);
-#pragma unroll 1
-    for (int c = 4 * threadIdx.x; c < C; c += 4 * LN_THREADS) {
-        const float4 w = ld4(p.ln_w + c), b = ld4(p.ln_b + c);
-        const float4 xx = ln_apply(*reinterpret_cast<const float4*>(row + c), mean, rstd, w, b);
-        const float4 pv = (prev_t >= 0) ? ln_apply(residual4(r, prev_t, c), pmean, prstd, w, b)
-                                        : ld4(p.shift_state + (size_t)slot * C + c);
-        float4 sx;
-        sx.x = pv.x - xx.x; sx.y = pv.y - xx.y; sx.z = pv.z - xx.z; sx.w = pv.w - xx.w;
-        *reinterpret_cast<float4*>(p.xx_out + (size_t)t * C + c) = xx;
-        if (p.sx_out) *reinterpret_cast<float4*>(p.sx_out + (size_t)t * C + c) = sx;
-#pragma unroll 1
-        for (int m = 0; m < p.n_mix; ++m) {
-            const float4 mu = ld4(p.mu[m] + c);
-            uint2 o;
-            o.x = pack_h2(xx.x + sx.x * mu.x, xx.y + sx.y * mu.y);
-            o.y = pack_h2(xx.z + sx.z * mu.z, xx.w + sx.w * mu.w);
-            *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t, c, p.kq_tile)) = o;
+    float4 a[NV], w[NV], b[NV], pv[NV];
+    stamp(1);
+    residual_row<NV>(r, t, a);
+    stamp(2);
+    // LN parameters and the shift state do not depend on this phase: request them before the
+    // reductions so their latency hides behind the two block sums
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = 4 * (threadIdx.x + LN_THREADS * j);
+        const bool ok = c < C;
+        w[j] = ok ? ld4(p.ln_w + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b[j] = ok ? ld4(p.ln_b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pv[j] = (ok && prev_t < 0) ? ld4(p.shift_state + (size_t)slot * C + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (p.x_out != p.x_in || p.n_parts > 0) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = 4 * (threadIdx.x + LN_THREADS * j);
+            if (c < C) *reinterpret_cast<float4*>(p.x_out + (size_t)t * C + c) = a[j];
         }
-        if (last && p.commit_dst)
-            *reinterpret_cast<float4*>(p.commit_dst + (size_t)slot * C + c) = ld4(p.commit_src + (size_t)t * C + c);
+    }
+    float mean, rstd;
+    stamp(3);
+    row_stats<NV, MEGA>(C, a, red, mean, rstd);
+    stamp(4);
+    if (prev_t >= 0) {          // multi-token slot (prefill): previous token's LN output, recomputed
+        float pmean, prstd;
+        residual_row<NV>(r, prev_t, pv);
+        row_stats<NV, MEGA>(C, pv, red, pmean, prstd);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) pv[j] = ln_apply(pv[j], pmean, prstd, w[j], b[j]);
+    }
+    float4 sx[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = 4 * (threadIdx.x + LN_THREADS * j);
+        a[j] = ln_apply(a[j], mean, rstd, w[j], b[j]);       // xx
+        sx[j].x = pv[j].x - a[j].x; sx[j].y = pv[j].y - a[j].y; sx[j].z = pv[j].z - a[j].z; sx[j].w = pv[j].w - a[j].w;
+        if (c < C) {
+            *reinterpret_cast<float4*>(p.xx_out + (size_t)t * C + c) = a[j];
+            if (p.sx_out) *reinterpret_cast<float4*>(p.sx_out + (size_t)t * C + c) = sx[j];
+            if (last && p.commit_dst)
+                *reinterpret_cast<float4*>(p.commit_dst + (size_t)slot * C + c) = ld4(p.commit_src + (size_t)t * C + c);
+        }
+    }
+    stamp(5);
+#pragma unroll 1
+    for (int m = 0; m < p.n_mix; ++m) {
+        const float* mup = p.mu[m];
+        __half* outp = p.mix_out[m];
+        float4 mu[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = 4 * (threadIdx.x + LN_THREADS * j);
+            mu[j] = (c < C) ? ld4(mup + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = 4 * (threadIdx.x + LN_THREADS * j);
+            if (c < C) {
+                uint2 o;
+                o.x = pack_h2(a[j].x + sx[j].x * mu[j].x, a[j].y + sx[j].y * mu[j].y);
+                o.y = pack_h2(a[j].z + sx[j].z * mu[j].z, a[j].w + sx[j].w * mu[j].w);
+                *reinterpret_cast<uint2*>(outp + a16_index(t, c, p.kq_tile)) = o;
+            }
+        }
     }
 }
 
+template <bool MEGA>
+__device__ __forceinline__ void ln_mix_row(const LnMixParams& p, const int t, float* red, unsigned long long* stamps = nullptr) {
+    const int nv = (p.C + 4 * LN_THREADS - 1) / (4 * LN_THREADS);
+    if (nv <= 1) ln_mix_row_nv<1, MEGA>(p, t, red);
+    else if (nv == 2) ln_mix_row_nv<2, MEGA>(p, t, red);
+    else if (nv <= 4 || MEGA) ln_mix_row_nv<4, MEGA>(p, t, red, stamps);      // the whole-step kernel caps C at 4096
+    else ln_mix_row_nv<8, MEGA>(p, t, red);
+    if (stamps && threadIdx.x == 0) stamps[6] = globaltimer_ns();
+}
+
 __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const __grid_constant__ LnMixParams p) {
-    extern __shared__ __align__(16) float ln_row[];
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
     const int t = blockIdx.x;
     if (t >= p.meta.T()) return;
-    ln_mix_row<false>(p, t, ln_row, red);
+    ln_mix_row<false>(p, t, red);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -176,44 +248,51 @@ struct EmbedParams {
     float* x_out;          // [T, C]
 };
 
-template <bool MEGA>
-__device__ __forceinline__ void embed_row(const EmbedParams& p, const int t, float* row, float* red) {
+template <int NV, bool MEGA>
+__device__ __forceinline__ void embed_row_nv(const EmbedParams& p, const int t, float* red) {
     const int C = p.C;
     int tok = p.meta.tok()[t];
     tok = min(max(tok, 0), p.V - 1);
-    float s = 0.f;
-#pragma unroll 1
-    for (int c = 4 * threadIdx.x; c < C; c += 4 * LN_THREADS) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(p.emb + (size_t)tok * C + c);
-        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
-        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
-        *reinterpret_cast<float4*>(row + c) = make_float4(lo.x, lo.y, hi.x, hi.y);
-        s += (lo.x + lo.y) + (hi.x + hi.y);
+    float4 a[NV], w[NV], b[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = 4 * (threadIdx.x + LN_THREADS * j);
+        if (c < C) {
+            const uint2 raw = *reinterpret_cast<const uint2*>(p.emb + (size_t)tok * C + c);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            a[j] = make_float4(lo.x, lo.y, hi.x, hi.y);
+            w[j] = ld4(p.ln_w + c);
+            b[j] = ld4(p.ln_b + c);
+        } else {
+            a[j] = w[j] = b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
-    const float mean = block_sum<MEGA>(s, red) / (float)C;
-    float s2 = 0.f;
-#pragma unroll 1
-    for (int c = 4 * threadIdx.x; c < C; c += 4 * LN_THREADS) {
-        const float4 a = *reinterpret_cast<const float4*>(row + c);
-        const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
-        s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    float mean, rstd;
+    row_stats<NV, MEGA>(C, a, red, mean, rstd);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = 4 * (threadIdx.x + LN_THREADS * j);
+        if (c < C) *reinterpret_cast<float4*>(p.x_out + (size_t)t * C + c) = ln_apply(a[j], mean, rstd, w[j], b[j]);
     }
-    const float var = block_sum<MEGA>(s2, red) / (float)C;
-    const float rstd = 1.0f / sqrtf(var + LN_EPS);
-#pragma unroll 1
-    for (int c = 4 * threadIdx.x; c < C; c += 4 * LN_THREADS)
-        *reinterpret_cast<float4*>(p.x_out + (size_t)t * C + c) =
-            ln_apply(*reinterpret_cast<const float4*>(row + c), mean, rstd, ld4(p.ln_w + c), ld4(p.ln_b + c));
+}
+
+template <bool MEGA>
+__device__ __forceinline__ void embed_row(const EmbedParams& p, const int t, float* red) {
+    const int nv = (p.C + 4 * LN_THREADS - 1) / (4 * LN_THREADS);
+    if (nv <= 1) embed_row_nv<1, MEGA>(p, t, red);
+    else if (nv == 2) embed_row_nv<2, MEGA>(p, t, red);
+    else if (nv <= 4 || MEGA) embed_row_nv<4, MEGA>(p, t, red);      // the whole-step kernel caps C at 4096
+    else embed_row_nv<8, MEGA>(p, t, red);
 }
 
 __global__ void __launch_bounds__(LN_THREADS) embed_ln0_kernel(const __grid_constant__ EmbedParams p) {
-    extern __shared__ __align__(16) float ln_row[];
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
     const int t = blockIdx.x;
     if (t >= p.meta.T()) return;
-    embed_row<false>(p, t, ln_row, red);
+    embed_row<false>(p, t, red);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -239,40 +318,63 @@ struct LnOutParams {
     float* hidden_out;      // optional [T, C]: updated residual (debug / states endpoint)
 };
 
-template <bool MEGA>
-__device__ __forceinline__ void ln_out_row(const LnOutParams& p, const int t, float* rowbuf, float* red) {
+template <int NV, bool MEGA>
+__device__ __forceinline__ void ln_out_row_nv(const LnOutParams& p, const int t, float* red) {
     const int C = p.C;
     const int slot = p.meta.tok_slot()[t];
     const bool last = p.meta.tok_last()[t] != 0;
     const int row = p.meta.tok_outrow()[t];
     if (last && p.commit_dst) {
-#pragma unroll 1
-        for (int c = 4 * threadIdx.x; c < C; c += 4 * LN_THREADS)
-            *reinterpret_cast<float4*>(p.commit_dst + (size_t)slot * C + c) = ld4(p.commit_src + (size_t)t * C + c);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int c = 4 * (threadIdx.x + LN_THREADS * j);
+            if (c < C) *reinterpret_cast<float4*>(p.commit_dst + (size_t)slot * C + c) = ld4(p.commit_src + (size_t)t * C + c);
+        }
     }
     if (row < 0 && !p.hidden_out) return;
     const ResidualSrc r = make_residual_src(p);
-    float mean, rstd;
-    ln_stats<MEGA>(r, t, rowbuf, p.hidden_out, red, mean, rstd);
+    float4 a[NV], w[NV], b[NV];
+    residual_row<NV>(r, t, a);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = 4 * (threadIdx.x + LN_THREADS * j);
+        const bool ok = c < C;
+        w[j] = ok ? ld4(p.ln_w + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b[j] = ok ? ld4(p.ln_b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && p.hidden_out) *reinterpret_cast<float4*>(p.hidden_out + (size_t)t * C + c) = a[j];
+    }
     if (row < 0) return;
-#pragma unroll 1
-    for (int c = 4 * threadIdx.x; c < C; c += 4 * LN_THREADS) {
-        const float4 y = ln_apply(*reinterpret_cast<const float4*>(rowbuf + c), mean, rstd, ld4(p.ln_w + c), ld4(p.ln_b + c));
-        uint2 o;
-        o.x = pack_h2(y.x, y.y);
-        o.y = pack_h2(y.z, y.w);
-        *reinterpret_cast<uint2*>(p.head_in + a16_index(row, c, p.kq_tile)) = o;
+    float mean, rstd;
+    row_stats<NV, MEGA>(C, a, red, mean, rstd);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int c = 4 * (threadIdx.x + LN_THREADS * j);
+        if (c < C) {
+            const float4 y = ln_apply(a[j], mean, rstd, w[j], b[j]);
+            uint2 o;
+            o.x = pack_h2(y.x, y.y);
+            o.y = pack_h2(y.z, y.w);
+            *reinterpret_cast<uint2*>(p.head_in + a16_index(row, c, p.kq_tile)) = o;
+        }
     }
 }
 
+template <bool MEGA>
+__device__ __forceinline__ void ln_out_row(const LnOutParams& p, const int t, float* red) {
+    const int nv = (p.C + 4 * LN_THREADS - 1) / (4 * LN_THREADS);
+    if (nv <= 1) ln_out_row_nv<1, MEGA>(p, t, red);
+    else if (nv == 2) ln_out_row_nv<2, MEGA>(p, t, red);
+    else if (nv <= 4 || MEGA) ln_out_row_nv<4, MEGA>(p, t, red);      // the whole-step kernel caps C at 4096
+    else ln_out_row_nv<8, MEGA>(p, t, red);
+}
+
 __global__ void __launch_bounds__(LN_THREADS) ln_out_kernel(const __grid_constant__ LnOutParams p) {
-    extern __shared__ __align__(16) float ln_row[];
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
     const int t = blockIdx.x;
     if (t >= p.meta.T()) return;
-    ln_out_row<false>(p, t, ln_row, red);
+    ln_out_row<false>(p, t, red);
 }
 
 }  // namespace b200

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128, 1) stream_ring_kernel(const __grid_consta
                 const uint32_t st = smem_base + stage * SB;
                 for (int blk = 0; blk < SB / 16384; ++blk)
                     for (int k16 = 0; k16 < 4; ++k16) {
-                        const uint64_t a_ = umma_desc(st + blk * 16384 + k16 * 2 * GEMM_W_LBO, GEMM_W_LBO, GEMM_W_SBO);
+                        const uint64_t a_ = umma_desc(st + blk * 16384 + k16 * 2 * 2048, 2048, 128);
                         const uint64_t b_ = umma_desc(st + k16 * 2 * GEMM_A_LBO, GEMM_A_LBO, GEMM_A_SBO);   // garbage operand, same smem
                         tc_mma_f16(tmem_base, a_, b_, IDESC, 1u);
                     }

@@ -73,9 +73,13 @@ struct WkvShared {
 // Runs the recurrence for `nt` tokens starting at token index t0 on head h with the state patch
 // m[4] (rows 4*ig+e, cols 4*j4..) in registers.  `w_local`: optional shared-memory decay rows
 // [token][64] (whole-step kernel, v6) indexed from local token `lt0`.
+// `pre`: optional shared-memory copy of the head's per-token vectors, [array][token][64] with arrays
+// r, k, v, g (, w, a, nu for v7) and `pre_stride` floats between arrays (whole-step kernel: gathered
+// once per WKV unit so the per-token loop never waits on L2).
 template <int VER, bool MEGA>
 __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const int t0, const int nt, float4 (&m)[4],
-                                         WkvShared& sm, const float* w_local, const int lt0) {
+                                         WkvShared& sm, const float* w_local, const int lt0, const float* pre = nullptr,
+                                         const int pre_stride = 0) {
     const int tid = threadIdx.x;
     const int ig = tid >> 4;           // value rows 4*ig .. 4*ig+3
     const int j4 = tid & 15;           // key cols  4*j4 .. 4*j4+3
@@ -91,13 +95,16 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
         // ---- per-token head vectors -> shared ----
         if (tid < WKV_N) {
             const int c = tid;
-            float r = p.r[row + c], k = p.k[row + c], v = p.v[row + c];
+            const int pi = (lt0 + tt) * WKV_N + c;
+            float r = pre ? pre[pi] : p.r[row + c];
+            float k = pre ? pre[pre_stride + pi] : p.k[row + c];
+            float v = pre ? pre[2 * pre_stride + pi] : p.v[row + c];
             float w;
             if (VER == 5) w = p.w_static[ch + c];
-            else if (w_local) w = w_local[(lt0 + tt) * WKV_N + c];
-            else w = p.w[row + c];
+            else if (w_local) w = w_local[pi];
+            else w = pre ? pre[4 * pre_stride + pi] : p.w[row + c];
             if (VER == 7) {
-                const float a = p.a[row + c];
+                const float a = pre ? pre[5 * pre_stride + pi] : p.a[row + c];
                 float kk = k * p.k_k[ch + c];
                 // l2 norm over the head: two warps
                 float ss = warp_sum(kk * kk);
@@ -107,7 +114,7 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
                 kk = kk / fmaxf(sqrtf(ss), 1e-12f);
                 k = k * (1.f + (a - 1.f) * p.k_a[ch + c]);
                 if (p.layer0) p.v_first[row + c] = v;
-                else v = v + (p.v_first[row + c] - v) * p.nu[row + c];
+                else v = v + (p.v_first[row + c] - v) * (pre ? pre[6 * pre_stride + pi] : p.nu[row + c]);
                 float bonus = warp_sum(r * k * p.r_k[ch + c]);
                 if ((tid & 31) == 0) sm.red[2 + (tid >> 5)] = bonus;
                 sm.b[c] = kk * a;       // kk (.) a
@@ -187,8 +194,9 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
                 y0 += bonus * sm.v[tid];
                 y1 += bonus * sm.v[tid + 32];
             }
-            y0 *= p.g[row + tid];
-            y1 *= p.g[row + tid + 32];
+            const int gi = (lt0 + tt) * WKV_N + tid;
+            y0 *= pre ? pre[3 * pre_stride + gi] : p.g[row + tid];
+            y1 *= pre ? pre[3 * pre_stride + gi + 32] : p.g[row + tid + 32];
             p.out[a16_index(t, ch + tid, p.kq_tile)] = f2h_sat(y0);
             p.out[a16_index(t, ch + tid + 32, p.kq_tile)] = f2h_sat(y1);
         }

@@ -75,13 +75,18 @@ int32_t b200rwkv_create(const uint8_t* st, size_t len, int32_t device, int32_t m
  * Every rank calls create_tp with the same model, then exchanges the opaque handle blobs
  * (b200rwkv_tp_export on each rank, all-gathered by the host over any side channel) and
  * passes all `world` blobs, rank-ordered, to b200rwkv_tp_connect.  After that every API call
- * is SPMD: all ranks make the same call with the same arguments. */
+ * is SPMD: all ranks make the same call with the same arguments.  Rank 0 receives the full
+ * [rows, num_vocab] logits (gathered from every rank's vocabulary shard over NVLink peer
+ * memory); the other ranks' logits_out may be NULL.  State tensors are sharded by head:
+ * state_back on rank r fills the WKV rows of its own heads and zeros elsewhere. */
 #define B200RWKV_TP_HANDLE_BYTES 128
 int32_t b200rwkv_create_tp(const uint8_t* st, size_t len, int32_t device, int32_t max_batch,
                            int32_t token_chunk_size, int32_t precision, int32_t rank, int32_t world,
                            b200rwkv_engine** out);
 int32_t b200rwkv_tp_export(b200rwkv_engine*, uint8_t handle_out[B200RWKV_TP_HANDLE_BYTES]);
 int32_t b200rwkv_tp_connect(b200rwkv_engine*, const uint8_t* handles /* world * HANDLE_BYTES */);
+/* Same wiring when all ranks live in one process (rank-ordered array of engines). */
+int32_t b200rwkv_tp_connect_local(b200rwkv_engine** engines, int32_t n);
 
 /* Dropping the `Arc<dyn Runtime>` (crates/ai00-core/src/lib.rs:600,654). */
 void b200rwkv_destroy(b200rwkv_engine*);

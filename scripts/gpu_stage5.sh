@@ -13,4 +13,4 @@ except Exception as e: print("ERR", l[-600:])
 PY
 done
 timeout 300 python scripts/gpu_trace.py 2>&1 | tail -34
-timeout 300 python scripts/gpu_gemmtime.py 2>&1 | tail -9 | cut -c1-330
+
