@@ -313,7 +313,7 @@ struct b200rwkv_engine {
     int S = 0, chunk = 0, maxT = 64;
     int L = 0, C = 0, F = 0, V = 0, H = 0, N = 64, Cl = 0, Hl = 0, Fl = 0, Vl = 0;
     bool use_graph = true, use_pdl = true;
-    bool use_mega = true, mega_ok = false;
+    bool use_mega = false, mega_ok = false;   // whole-step kernel is opt-in (B200RWKV_MEGA=1): see DESIGN.md, measured slower in round 1
     MegaParams mega;
     std::vector<int> mega_phase_types;
     int split_att = 1, split_ffn = 1;
@@ -501,6 +501,7 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
     g.grid = std::max(1, std::min(num_sms, std::max(tile, cdiv(blk, 4))));
     g.grid = std::min(g.grid, blk);
     if (force_grid > 0) g.grid = std::min(force_grid, blk);
+    else if (tile <= num_sms && tile * 10 >= num_sms * 9) g.grid = tile;   // one whole tile per CTA: no cross-CTA fix-up
     const int per_cta = std::max(1, blk / g.grid);
     g.p.max_contrib = cdiv(kbmax, per_cta) + 1;
     g.p.counters = (unsigned*)dalloc((size_t)tile * 4, true);
@@ -975,7 +976,7 @@ void b200rwkv_engine::build_mega(const StFile& st) {
     if (!use_mega) return;
     if (ver == 6 && (Dd > MEGA_MAX_DD || Dd % 8 != 0)) return;
     if (C > MEGA_MAX_C) return;
-    mega_lora_cc = (ver == 6) && !getenv("B200RWKV_LORA_GEMM") && info.time_mix_adapter % 8 == 0 &&
+    mega_lora_cc = (ver == 6) && getenv("B200RWKV_LORA_CC") && info.time_mix_adapter % 8 == 0 &&
                    5 * info.time_mix_adapter <= num_sms * LORA_MAX_ROWS_PER_CTA;
     auto upload_raw = [&](const StTensor& t) {
         __half* d = (__half*)dalloc(t.nbytes, false);

@@ -182,7 +182,7 @@ class Model:
 
     # ---- raw call: one b200rwkv_infer ----
     def infer_raw(self, slots, ntok, tokens, options, out: np.ndarray | None = None):
-        V = self.info["num_vocab"] // self.world
+        V = self.info["num_vocab"]          # rank 0 receives the gathered full-vocabulary rows
         n = len(slots)
         total = sum(nt if o == capi.OPTION_FULL else (1 if (o == capi.OPTION_LAST and nt > 0) else 0)
                     for nt, o in zip(ntok, options))

@@ -206,8 +206,7 @@ def main():
     value = BATCH * args.steps / (ms * 1e-3)
 
     # ---- e2e: host tokens in, host logits out, every step, through Runtime.infer ----
-    V_local = shape.V // world
-    out = np.empty((BATCH, V_local), np.float32)
+    out = np.empty((BATCH, shape.V), np.float32)       # rank 0 receives the gathered full-vocabulary logits
     try:
         tt = torch.from_numpy(out)
         torch.cuda.cudart().cudaHostRegister(tt.data_ptr(), out.nbytes, 0)     # pinned host memory
@@ -231,11 +230,7 @@ def main():
            "h2d_bytes_per_step": int((8 + 6 * 64 + 3 * BATCH) * 4), "d2h_bytes_per_step": int(out.nbytes),
            "api": "runtime.Model.infer_raw -> b200rwkv_infer (host token ids in, host f32 logits out, wall clock)"}
 
-    if rank != 0:
-        model.close()
-        return
-
-    # ---- roofline of the dominant kernel (projection GEMM) ----
+    # ---- roofline of the dominant kernel (projection GEMM); SPMD under tensor parallelism ----
     peaks, peak_src = read_peaks()
     prof_ms = np.zeros(4)
     prof_n = np.zeros(4, dtype=np.int64)
@@ -248,15 +243,23 @@ def main():
         prof_ms += np.array(m4)
         prof_n = np.array(n4)
     prof_ms /= reps
+    if rank != 0:
+        barrier()
+        model.close()
+        return
     gemm_gbs = wbytes / (prof_ms[0] * 1e-3) / 1e9 if prof_ms[0] > 0 else 0.0
     alg_bytes = synth.algorithmic_bytes_per_step(shape, BATCH) / world
-    roofline = {"bound": "hbm", "kernel": "gemm_kernel<1> (all projection launches of one step)",
+    roofline = {"bound": "hbm", "kernel": "gemm_kernel<1> (tcgen05 projection GEMM: all launches of one step, per GPU)",
                 "achieved": gemm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gemm_gbs / peaks["hbm_gbs"],
                 "peak_source": f"MEASURED_PEAKS.json ({peak_src})", "traffic": None,
                 "algorithmic_bytes_per_step_gemm": int(wbytes), "gemm_ms_per_step": float(prof_ms[0]),
                 "gemm_launches_per_step": int(prof_n[0]),
-                "class_ms_per_step": {"gemm": float(prof_ms[0]), "wkv": float(prof_ms[1]), "ln_mix": float(prof_ms[2])},
-                "class_launches_per_step": {"gemm": int(prof_n[0]), "wkv": int(prof_n[1]), "ln_mix": int(prof_n[2])},
+                "note": "per-launch CUDA events on the engine stream in an un-graphed pass (includes launch gaps); "
+                        "step_frac is the whole captured step against the same peak",
+                "class_ms_per_step": {"gemm": float(prof_ms[0]), "wkv": float(prof_ms[1]), "ln_mix": float(prof_ms[2]),
+                                      "other": float(prof_ms[3])},
+                "class_launches_per_step": {"gemm": int(prof_n[0]), "wkv": int(prof_n[1]), "ln_mix": int(prof_n[2]),
+                                            "other": int(prof_n[3])},
                 "step_algorithmic_bytes": int(alg_bytes),
                 "step_achieved_gbs": alg_bytes / (ms_per_step * 1e-3) / 1e9,
                 "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]}
@@ -277,6 +280,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "build_seconds": build_s}
     print(json.dumps(line))
+    barrier()
     model.close()
 
 

@@ -241,6 +241,7 @@ def test_whole_step_kernel_equals_per_op_kernels(models, preset):
     decay LoRA stage 2 in a different summation order)."""
     a, orc, _ = models(preset, mega=True)
     b, _, _ = models(preset, mega=False)
+    assert a is not b
     rng = np.random.default_rng(21)
     st = (rng.standard_normal(a.state.init().shape) * 0.3).astype(np.float32)
     runs = [rng.integers(1, 500, size=n).tolist() for n in (3, 1, 5, 2)]
@@ -263,10 +264,11 @@ def test_whole_step_kernel_equals_per_op_kernels(models, preset):
     assert la.shape == lb.shape
 
 
-@pytest.mark.parametrize("preset", ["small6", "tiny7"])
+@pytest.mark.parametrize("preset", ["small6"])
 def test_tensor_parallel_two_ranks_in_process(preset):
     """Head/column tensor parallelism, world = 2, both ranks in this process on one GPU (per-op
-    kernels: two whole-GPU cooperative kernels cannot share a device).  TP-degree invariance:
+    kernels: two whole-GPU cooperative kernels cannot share a device; the deployment shape, one
+    process per GPU, is covered by tests/test_gpu_tp_multiproc.py).  TP-degree invariance:
     same argmax, logits within tolerance of the single-rank engine; rank 0 receives the full
     vocabulary, gathered from both shards."""
     from ai00_server_b200 import tp
