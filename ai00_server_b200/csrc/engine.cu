@@ -387,8 +387,10 @@ struct b200rwkv_engine {
     std::vector<SmallKParams> mega_smallks;
     void launch_mega(cudaStream_t s);
 
-    template <typename P>
-    void launch_k(void (*kern)(P), dim3 grid, dim3 block, size_t smem, const P& params, int cls, cudaStream_t s, Profiler* prof);
+    template <typename P, typename... X>
+    void launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, size_t smem, const P& params, int cls, cudaStream_t s, Profiler* prof,
+                  X... extra);
+    bool fold_wd2 = false;
     void launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof);
     void enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* prof);
     void run_step(int MT, int MTR);
@@ -513,9 +515,9 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
     return g;
 }
 
-template <typename P>
-void b200rwkv_engine::launch_k(void (*kern)(P), dim3 grid, dim3 block, size_t smem, const P& params, int cls, cudaStream_t s,
-                               Profiler* prof) {
+template <typename P, typename... X>
+void b200rwkv_engine::launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, size_t smem, const P& params, int cls, cudaStream_t s,
+                               Profiler* prof, X... extra) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
@@ -533,7 +535,7 @@ void b200rwkv_engine::launch_k(void (*kern)(P), dim3 grid, dim3 block, size_t sm
         CK(cudaEventCreate(&eb));
         CK(cudaEventRecord(ea, s));
     }
-    CK(cudaLaunchKernelEx(&cfg, kern, params));
+    CK(cudaLaunchKernelEx(&cfg, kern, params, extra...));
     if (prof) {
         CK(cudaEventRecord(eb, s));
         prof->recs.push_back({cls, ea, eb});
@@ -765,6 +767,24 @@ void b200rwkv_engine::build(const StFile& st) {
                 ly.wd2_index = (int)ly.pre.size();
                 ly.pre.push_back(make_launch(sv));
             }
+            if (Dd <= 128 && Dd % 8 == 0 && !getenv("B200RWKV_NOFOLD")) {
+                // k-major copy of this rank's time_decay_w2 rows, one contiguous [Dd][64] slice per head: the WKV
+                // kernels evaluate the decay LoRA stage 2 themselves (one launch / phase less per layer)
+                const StTensor& t = st.get(a + "time_decay_w2");
+                const __half* src = reinterpret_cast<const __half*>(t.data);
+                std::vector<__half> tmp((size_t)Hl * Dd * 64);
+                for (int h = 0; h < Hl; ++h)
+                    for (int k = 0; k < Dd; ++k)
+                        for (int c = 0; c < 64; ++c) tmp[((size_t)h * Dd + k) * 64 + c] = src[(size_t)(c0 + h * 64 + c) * Dd + k];
+                __half* dw = (__half*)dalloc(tmp.size() * 2, false);
+                CK(cudaMemcpy(dw, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));
+                wk.wd2t = dw;
+                wk.decay_bias = ly.pre[ly.wd2_index].p.seg[0].bias;
+                wk.d1 = a_lora[1].p;
+                wk.d1_kq = a_lora[1].kq;
+                wk.Dd = Dd;
+                fold_wd2 = true;
+            }
             wk.w = f_w;
             wk.u = vec_f32(st, a + "time_first", c0, Cl);
         } else if (ver == 5) {
@@ -987,24 +1007,7 @@ void b200rwkv_engine::build_mega(const StFile& st) {
     for (int l = 0; l < L; ++l) {
         Layer& ly = layers[l];
         WkvParams w = ly.wkv;
-        if (ver == 6) {
-            // k-major copy of this rank's time_decay_w2 rows, one contiguous [Dd][64] slice per head
-            const StTensor& t = st.get("blocks." + std::to_string(l) + ".att.time_decay_w2");
-            REQUIRE(t.shape.size() == 2 && t.shape[0] == C && t.shape[1] == Dd, B200RWKV_ERR_INVALID, "time_decay_w2 shape");
-            const __half* src = reinterpret_cast<const __half*>(t.data);
-            std::vector<__half> tmp((size_t)Hl * Dd * 64);
-            const int c0 = rank * Cl;
-            for (int h = 0; h < Hl; ++h)
-                for (int k = 0; k < Dd; ++k)
-                    for (int c = 0; c < 64; ++c) tmp[((size_t)h * Dd + k) * 64 + c] = src[(size_t)(c0 + h * 64 + c) * Dd + k];
-            __half* d = (__half*)dalloc(tmp.size() * 2, false);
-            CK(cudaMemcpy(d, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));
-            w.wd2t = d;
-            w.decay_bias = ly.pre[ly.wd2_index].p.seg[0].bias;
-            w.d1 = a_lora[1].p;
-            w.d1_kq = a_lora[1].kq;
-            w.Dd = Dd;
-        }
+        if (ver == 6 && !w.wd2t) return;      // decay LoRA not folded: this path needs it
         mega_wkvs.push_back(w);
         if (mega_lora_cc) {
             // ddlerp LoRA on CUDA cores: no cross-CTA reduction (lora.cuh)
@@ -1137,11 +1140,13 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
     for (int l = 0; l < L; ++l) {
         Layer& ly = layers[l];
         if (!(sk & 1)) launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, ly.ln1, KC_LN, s, prof);
-        for (auto& g : ly.pre) gemm(g);
+        for (int gi = 0; gi < (int)ly.pre.size(); ++gi)
+            if (!(fold_wd2 && gi == ly.wd2_index)) gemm(ly.pre[gi]);
+        const size_t wkv_smem = fold_wd2 ? wkv_fold_smem_bytes(info.time_decay_adapter, maxT) : 0;
         if (!(sk & 4)) switch (info.version) {
-            case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof); break;
-            case 6: launch_k(wkv_kernel<6>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof); break;
-            default: launch_k(wkv_kernel<7>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof); break;
+            case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof, maxT); break;
+            case 6: launch_k(wkv_kernel<6>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), wkv_smem, ly.wkv, KC_WKV, s, prof, maxT); break;
+            default: launch_k(wkv_kernel<7>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof, maxT); break;
         }
         gemm(ly.o);
         if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
@@ -1656,14 +1661,7 @@ int32_t b200rwkv_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_t* 
     CK(cudaEventRecord(eb, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(ms_out, ea, eb));
-    if (launches_out) {
-        // kernels per step are fixed by the schedule; count them from one un-captured enqueue on a scratch pass
-        long long per_step = 1;   // embed
-        for (auto& ly : e->layers) per_step += 1 + (long long)ly.pre.size() + 1 + 1 + 1 + (long long)ly.ffn.size();
-        per_step += 2;            // ln_out + head
-        if (e->mega_ok && MT == 1) per_step = 1;   // whole step = one persistent kernel
-        *launches_out = per_step * steps;
-    }
+    if (launches_out) *launches_out = (int64_t)e->launches_last_step * steps;   // counted when the step was enqueued / captured
     CK(cudaEventDestroy(ea));
     CK(cudaEventDestroy(eb));
     if (flush) CK(cudaFree(flush));

@@ -247,19 +247,32 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[mt][j] = 0.f;
-                for (int s = 0; s < ncontrib; ++s) {           // fixed order -> deterministic
-                    const float* w_ = ws0 + (size_t)s * (GEMM_BN * ROWF);
+                // fixed slot order -> deterministic; four contributors' loads in flight at a time
+                constexpr int UB = (MT >= 4) ? 1 : (MT == 2 ? 2 : 4);
+                for (int s0 = 0; s0 < ncontrib; s0 += UB) {
+                    float4 pv[UB][MT][4];
 #pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
+                    for (int u = 0; u < UB; ++u) {
+                        const float* w_ = ws0 + (size_t)(s0 + u) * (GEMM_BN * ROWF);
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 a = __ldcg(reinterpret_cast<const float4*>(w_ + mt * 16 + j));
-                            v[mt][j] += a.x; v[mt][j + 1] += a.y; v[mt][j + 2] += a.z; v[mt][j + 3] += a.w;
-                        }
+                        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                pv[u][mt][j] = (s0 + u < ncontrib) ? __ldcg(reinterpret_cast<const float4*>(w_ + mt * 16 + 4 * j))
+                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u)
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                v[mt][4 * j] += pv[u][mt][j].x; v[mt][4 * j + 1] += pv[u][mt][j].y;
+                                v[mt][4 * j + 2] += pv[u][mt][j].z; v[mt][4 * j + 3] += pv[u][mt][j].w;
+                            }
                 }
             }
         }
-        stamp(10);
         if (do_epilogue) {
             // The segment descriptor lives in kernel-parameter space (stand-alone kernel) or global
             // memory (whole-step kernel): hoist every field the loop needs into registers once.
@@ -293,13 +306,25 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
                     }
                     const float mu = (out_mode == OUT_LERP_A16) ? aux2[n] : 0.f;
 #pragma unroll 1
-                    for (int m = 0; m < mmax; ++m) {
-                        float y = apply_act(lv[m] + bias, act);
-                        if (out_mode == OUT_LERP_A16) {
-                            const size_t a_ = (size_t)m * ld_aux + n;
-                            y = aux0[a_] + aux1[a_] * (mu + y);
+                    for (int m0 = 0; m0 < mmax; m0 += 4) {
+                        // the two lerp operands of four tokens are requested together (L2 latency bound)
+                        float x0[4], x1[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const bool ok = (out_mode == OUT_LERP_A16) && (m0 + u < mmax);
+                            const size_t a_ = (size_t)(m0 + u) * ld_aux + n;
+                            x0[u] = ok ? aux0[a_] : 0.f;
+                            x1[u] = ok ? aux1[a_] : 0.f;
                         }
-                        base[a16_index(m, nn, ldo)] = f2h_sat(y);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int m = m0 + u;
+                            if (m < mmax) {
+                                float y = apply_act(lv[m] + bias, act);
+                                if (out_mode == OUT_LERP_A16) y = x0[u] + x1[u] * (mu + y);
+                                base[a16_index(m, nn, ldo)] = f2h_sat(y);
+                            }
+                        }
                     }
                 }
             }

@@ -204,14 +204,29 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
     }
 }
 
+// dynamic shared memory of the stand-alone kernel when the v6 decay LoRA stage 2 is folded in:
+// [Dd][64] halves (k-major slice of time_decay_w2) | [max tokens][64] floats (decays) | [Dd] halves | [4][64] floats
+__host__ __device__ inline size_t wkv_fold_smem_bytes(int Dd, int max_tokens) {
+    return (size_t)WKV_N * Dd * 2 + (size_t)max_tokens * WKV_N * 4 + (size_t)Dd * 2 + 4 * WKV_N * 4 + 64;
+}
+
 template <int VER>
-__global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant__ WkvParams p) {
+__global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant__ WkvParams p, const int max_tokens) {
     __shared__ WkvShared sm;
+    extern __shared__ __align__(16) uint8_t wkv_dyn[];
     pdl_launch_dependents();
     const int si = blockIdx.y;
     const int h = blockIdx.x;
     const int tid = threadIdx.x;
     const int ig = tid >> 4, j4 = tid & 15;
+    const bool fold = (VER == 6) && p.wd2t != nullptr;
+    // the decay-LoRA slice is a weight: fetch it before waiting on the producer kernel
+    __half* wt = reinterpret_cast<__half*>(wkv_dyn);
+    if (fold) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.wd2t + (size_t)h * WKV_N * p.Dd);
+        uint4* dst = reinterpret_cast<uint4*>(wt);
+        for (int i = tid; i < WKV_N * p.Dd / 8; i += WKV_THREADS) dst[i] = src[i];
+    }
     pdl_wait();
     if (si >= p.meta.nslots()) return;
     const int slot = p.meta.slot_id()[si];
@@ -222,7 +237,34 @@ __global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant_
     float4 m[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) m[e] = __ldcs(reinterpret_cast<const float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4));
-    wkv_slot<VER, false>(p, h, t0, nt, m, sm, nullptr, 0);
+
+    const float* w_local = nullptr;
+    if (fold) {
+        // w[t][c] = exp(-exp(time_decay[c] + sum_k Wd2[c][k] * tanh(Wd1 xw)[t][k]))   
+        const int Dd = p.Dd;
+        float* wl = reinterpret_cast<float*>(wkv_dyn + (size_t)WKV_N * Dd * 2);
+        __half* ds = reinterpret_cast<__half*>(wl + (size_t)max_tokens * WKV_N);
+        float* part = reinterpret_cast<float*>(wkv_dyn + (size_t)WKV_N * Dd * 2 + (size_t)max_tokens * WKV_N * 4 + (((size_t)Dd * 2 + 15) & ~(size_t)15));
+        const int c = tid & (WKV_N - 1), qk = tid >> 6;
+        const int kq0 = qk * (Dd >> 2), kq1 = kq0 + (Dd >> 2);
+        const float bias = p.decay_bias[h * WKV_N + c];
+        for (int tt = 0; tt < nt; ++tt) {
+            __syncthreads();
+            for (int k = tid; k < Dd; k += WKV_THREADS) ds[k] = p.d1[a16_index(t0 + tt, k, p.d1_kq)];
+            __syncthreads();
+            float acc = 0.f;
+            for (int k = kq0; k < kq1; ++k) acc = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(ds[k]), acc);
+            part[qk * WKV_N + c] = acc;
+            __syncthreads();
+            if (tid < WKV_N) {
+                const float s = (part[c] + part[WKV_N + c]) + (part[2 * WKV_N + c] + part[3 * WKV_N + c]);
+                wl[tt * WKV_N + c] = expf(-expf(bias + s));
+            }
+        }
+        __syncthreads();
+        w_local = wl;
+    }
+    wkv_slot<VER, false>(p, h, t0, nt, m, sm, w_local, 0);
 #pragma unroll
     for (int e = 0; e < 4; ++e) __stcs(reinterpret_cast<float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4), m[e]);
 }
