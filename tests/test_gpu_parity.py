@@ -264,6 +264,9 @@ def test_whole_step_kernel_equals_per_op_kernels(models, preset):
     assert la.shape == lb.shape
 
 
+@pytest.mark.skipif(os.environ.get("B200RWKV_TEST_INPROC_TP") != "1",
+                    reason="two ranks on ONE GPU need the driver to co-schedule both streams; opt-in (a stalled rendezvous "
+                           "trips the device watchdog and kills the context); tests/test_gpu_tp_multiproc.py is the real check")
 @pytest.mark.parametrize("preset", ["small6"])
 def test_tensor_parallel_two_ranks_in_process(preset):
     """Head/column tensor parallelism, world = 2, both ranks in this process on one GPU (per-op

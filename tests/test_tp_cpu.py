@@ -60,6 +60,6 @@ def test_handle_all_gather_over_gloo_world2(tmp_path):
     """))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(script)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
