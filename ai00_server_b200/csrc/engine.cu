@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "lora.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
 #include "mix.cuh"
@@ -390,7 +391,7 @@ struct b200rwkv_engine {
     template <typename P, typename... X>
     void launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, size_t smem, const P& params, int cls, cudaStream_t s, Profiler* prof,
                   X... extra);
-    bool fold_wd2 = false;
+    bool fold_wd2 = false, gemm_half = false, lora_cc = false;
     void launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof);
     void enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* prof);
     void run_step(int MT, int MTR);
@@ -545,7 +546,10 @@ void b200rwkv_engine::launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, siz
 
 void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof) {
     switch (MT) {
-        case 1: launch_k(gemm_kernel<1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
+        case 1:
+            if (gemm_half) launch_k(gemm_kernel<1, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, true>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            else launch_k(gemm_kernel<1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            break;
         case 2: launch_k(gemm_kernel<2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<2>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
         default: launch_k(gemm_kernel<4>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<4>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
     }
@@ -580,6 +584,9 @@ void b200rwkv_engine::build(const StFile& st) {
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&sm_stream, cudaStreamNonBlocking));
     CK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, true>::SMEM_BYTES));
+    if (const char* v = getenv("B200RWKV_GEMM_HALF")) gemm_half = atoi(v) != 0;
+    if (const char* v = getenv("B200RWKV_LORA_CC")) lora_cc = atoi(v) != 0;
     CK(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<4>::SMEM_BYTES));
 
@@ -993,10 +1000,10 @@ void b200rwkv_engine::build_mega(const StFile& st) {
     mega_prepared = false;
     const int ver = info.version;
     const int Dd = info.time_decay_adapter;
-    if (!use_mega) return;
+    if (!use_mega && !lora_cc) return;
     if (ver == 6 && (Dd > MEGA_MAX_DD || Dd % 8 != 0)) return;
     if (C > MEGA_MAX_C) return;
-    mega_lora_cc = (ver == 6) && getenv("B200RWKV_LORA_CC") && info.time_mix_adapter % 8 == 0 &&
+    mega_lora_cc = (ver == 6) && lora_cc && info.time_mix_adapter % 8 == 0 && info.time_mix_adapter <= 512 / 1 &&
                    5 * info.time_mix_adapter <= num_sms * LORA_MAX_ROWS_PER_CTA;
     auto upload_raw = [&](const StTensor& t) {
         __half* d = (__half*)dalloc(t.nbytes, false);
@@ -1041,7 +1048,7 @@ void b200rwkv_engine::build_mega(const StFile& st) {
 // Part 2 (after the tensor-parallel wiring): the device-side phase program.
 void b200rwkv_engine::build_mega_program() {
     mega_ok = false;
-    if (!mega_prepared) return;
+    if (!mega_prepared || !use_mega) return;
     const int ver = info.version;
     std::vector<Phase> phases;
     std::vector<LnMixParams> lns;
@@ -1140,8 +1147,18 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
     for (int l = 0; l < L; ++l) {
         Layer& ly = layers[l];
         if (!(sk & 1)) launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, ly.ln1, KC_LN, s, prof);
-        for (int gi = 0; gi < (int)ly.pre.size(); ++gi)
-            if (!(fold_wd2 && gi == ly.wd2_index)) gemm(ly.pre[gi]);
+        for (int gi = 0; gi < (int)ly.pre.size(); ++gi) {
+            if (fold_wd2 && gi == ly.wd2_index) continue;
+            if (lora_cc && MT == 1 && l < (int)mega_smallns.size() && gi == 0) {
+                if (!(sk & 2)) launch_k(smalln_kernel, dim3(std::min(num_sms, mega_smallns[l].N)), dim3(CONSUMER_THREADS), 0, mega_smallns[l], KC_OTHER, s, prof);
+                continue;
+            }
+            if (lora_cc && MT == 1 && l < (int)mega_smallks.size() && gi == 1) {
+                if (!(sk & 2)) launch_k(smallk_kernel, dim3(num_sms), dim3(CONSUMER_THREADS), (size_t)16 * 512 * 4, mega_smallks[l], KC_OTHER, s, prof);
+                continue;
+            }
+            gemm(ly.pre[gi]);
+        }
         const size_t wkv_smem = fold_wd2 ? wkv_fold_smem_bytes(info.time_decay_adapter, maxT) : 0;
         if (!(sk & 4)) switch (info.version) {
             case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof, maxT); break;

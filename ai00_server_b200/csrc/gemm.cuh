@@ -89,10 +89,13 @@ struct GemmParams {
     GemmSeg seg[GEMM_MAX_SEG];
 };
 
-template <int MT>
+// HALF: ring sized to half an SM's shared memory, so the NEXT projection launch (programmatic
+// dependent launch) can be resident and prefetching its first weight blocks while this one drains
+template <int MT, bool HALF = false>
 struct GemmCfg {
     static constexpr int STAGE_BYTES = GEMM_WBYTES + MT * GEMM_ABYTES;
-    static constexpr int NSTAGE = (GEMM_SMEM_BUDGET / STAGE_BYTES) > 12 ? 12 : (GEMM_SMEM_BUDGET / STAGE_BYTES);
+    static constexpr int BUDGET = HALF ? (GEMM_SMEM_BUDGET / 2) : GEMM_SMEM_BUDGET;
+    static constexpr int NSTAGE = (BUDGET / STAGE_BYTES) > 12 ? 12 : (BUDGET / STAGE_BYTES);
     static constexpr int BAR_BYTES = (2 * NSTAGE + 4) * 8 + 16;
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + BAR_BYTES + 64;
     static constexpr int TMEM_COLS = (2 * 16 * MT) < 32 ? 32 : (2 * 16 * MT);   // double-buffered accumulator
@@ -336,9 +339,9 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
 // ---------------------------------------------------------------------------------------
 // stand-alone kernel: warps 0-3 epilogue, warp 4 MMA issuer (+ TMEM allocation), warp 5 TMA producer
 // ---------------------------------------------------------------------------------------
-template <int MT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<MT>;
+template <int MT, bool HALF = false>
+__global__ void __launch_bounds__(GEMM_THREADS, HALF ? 2 : 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<MT, HALF>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int s_last;
     const uint32_t smem_base = smem_u32(smem);

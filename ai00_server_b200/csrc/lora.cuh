@@ -215,4 +215,18 @@ __device__ __forceinline__ void smallk_phase(const SmallKParams& p, const int ct
     }
 }
 
+// stand-alone launches of the same phases (per-op kernel chain)
+__global__ void __launch_bounds__(CONSUMER_THREADS) smalln_kernel(const __grid_constant__ SmallNParams p) {
+    __shared__ float scratch[LORA_MAX_ROWS_PER_CTA * 8 * 16];
+    pdl_launch_dependents();
+    pdl_wait();
+    smalln_phase<false>(p, blockIdx.x, gridDim.x, scratch);
+}
+__global__ void __launch_bounds__(CONSUMER_THREADS) smallk_kernel(const __grid_constant__ SmallKParams p) {
+    extern __shared__ __align__(16) float lora_in_s[];
+    pdl_launch_dependents();
+    pdl_wait();
+    smallk_phase<false>(p, blockIdx.x, gridDim.x, lora_in_s);
+}
+
 }  // namespace b200

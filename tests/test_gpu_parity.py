@@ -29,16 +29,19 @@ def rel_err(a, b):
 def models():
     cache = {}
 
-    def get(preset, seed=0, max_batch=4, chunk=32, mega=True, **over):
-        key = (preset, seed, max_batch, chunk, mega, tuple(sorted(over.items())))
+    def get(preset, seed=0, max_batch=4, chunk=32, mega=True, env=None, **over):
+        key = (preset, seed, max_batch, chunk, mega, tuple(sorted((env or {}).items())), tuple(sorted(over.items())))
         if key not in cache:
             shp = synth.PRESETS[preset] if not over else dataclasses.replace(synth.PRESETS[preset], **over)
             st = synth.make_st(shp, seed)
             os.environ["B200RWKV_MEGA"] = "1" if mega else "0"     # read at engine creation
+            os.environ.update(env or {})
             try:
                 m = runtime.Model(st, max_batch=max_batch, token_chunk_size=chunk)
             finally:
                 os.environ.pop("B200RWKV_MEGA", None)
+                for k in (env or {}):
+                    os.environ.pop(k, None)
             cache[key] = (m, O.Oracle(O.parse_st(st), "f16"), st)
         return cache[key]
 
@@ -307,3 +310,20 @@ def test_tensor_parallel_two_ranks_in_process(preset):
     assert rel_err(merged, sw) <= REL_TOL
     for m in [single] + ranks:
         m.close()
+
+
+@pytest.mark.parametrize("env", [{"B200RWKV_LORA_CC": "1"}, {"B200RWKV_GEMM_HALF": "1"}, {"B200RWKV_NOFOLD": "1", "B200RWKV_NOSPLIT": "1"}])
+def test_kernel_variants_match_oracle(models, env):
+    """Alternative kernel choices of the per-op chain (CUDA-core LoRA kernels, half-ring GEMM, un-folded decay
+    LoRA / stream-K fix-up instead of split-K) compute the same model."""
+    m, orc, _ = models("small6", mega=False, env=env)
+    rng = np.random.default_rng(9)
+    toks = rng.integers(1, 2000, size=(6, 3))
+    sts = [orc.state_init() for _ in range(3)]
+    for s in range(3):
+        m.state.load(m.state.init(), s)
+    for i in range(6):
+        rows = m.infer_raw([0, 1, 2], [1, 1, 1], toks[i].tolist(), [capi.OPTION_LAST] * 3)
+        for s in range(3):
+            want, sts[s] = orc.run([int(toks[i, s])], sts[s])
+            assert rel_err(rows[s], want) <= REL_TOL and rows[s].argmax() == want.argmax()
