@@ -120,6 +120,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
     SpinGuard g;
     while (!mbar_try(bar, parity)) g.poll(WD_MBAR, bar, parity, tag);
 }
+// fire-and-forget request to bring [p, p + bytes) into L2 (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // L2 policy for streamed-once weights
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     uint64_t pol;
@@ -248,6 +252,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 
 // Programmatic dependent launch: everything before this call may overlap the tail of the
 // preceding kernel in the stream/graph (weights are immutable, so weight prefetch may).
+// profiling aid: globaltimer stamp i of this launch's trace row (CTA 0, thread 0 only; `tr` is null in production)
+__device__ __forceinline__ void trace_stamp(unsigned long long* tr, const int i) {
+    if (tr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        tr[i] = t;
+    }
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

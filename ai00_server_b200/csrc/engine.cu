@@ -19,6 +19,7 @@
 
 #include "gemm.cuh"
 #include "lora.cuh"
+#include "pre6.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
 #include "mix.cuh"
@@ -295,6 +296,10 @@ struct Layer {
     WkvParams wkv;
     GemmLaunch o;
     std::vector<GemmLaunch> ffn;    // launches after LN2
+    // v6 decode front half as one launch (pre6.cuh): row-major copies of the ddlerp LoRA weights
+    const __half* w1_raw = nullptr;
+    const __half* w2_raw = nullptr;
+    const float* mu5[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct Profiler {
@@ -391,7 +396,24 @@ struct b200rwkv_engine {
     template <typename P, typename... X>
     void launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, size_t smem, const P& params, int cls, cudaStream_t s, Profiler* prof,
                   X... extra);
-    bool fold_wd2 = false, gemm_half = false, lora_cc = false;
+    bool fold_wd2 = false, lora_cc = false;
+    int gemm_ring = 2;            // GemmCfg RING mode of the decode-shaped projection kernel
+    int prefetch_blocks = 16;     // L2 prefetch depth (32 KB blocks per CTA) into the next projection launch
+    bool fused_pre = true, ln_cluster = true;     // decode-shaped cluster kernels of pre6.cuh
+    bool fused_pre_ok = false, ln_cluster_ok = false;
+    unsigned* pre_gbar = nullptr;
+    int launch_cluster = 0;                       // consumed by the next launch_k
+    // profiling aid (B200RWKV_STEP_TRACE=1): 8 globaltimer stamps of CTA 0 per launch of the per-op chain
+    unsigned long long* d_step_trace = nullptr;
+    std::vector<int> step_trace_types;
+    static constexpr int STEP_TRACE_MAX = 1024;
+    static constexpr int STEP_TRACE_ROW = 512;     // 8 stamps of CTA 0 + {SM id, last MMA, exit} of every projection CTA
+    unsigned long long* tr_next(int label) {
+        if (!d_step_trace || launches_last_step >= STEP_TRACE_MAX) return nullptr;
+        if ((int)step_trace_types.size() <= launches_last_step) step_trace_types.resize(launches_last_step + 1);
+        step_trace_types[launches_last_step] = label;
+        return d_step_trace + (size_t)STEP_TRACE_ROW * launches_last_step;
+    }
     void launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof);
     void enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* prof);
     void run_step(int MT, int MTR);
@@ -504,7 +526,15 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
     g.grid = std::max(1, std::min(num_sms, std::max(tile, cdiv(blk, 4))));
     g.grid = std::min(g.grid, blk);
     if (force_grid > 0) g.grid = std::min(force_grid, blk);
-    else if (tile <= num_sms && tile * 10 >= num_sms * 9) g.grid = tile;   // one whole tile per CTA: no cross-CTA fix-up
+    else if (!getenv("B200RWKV_OLD_GRID")) {
+        // Whole tiles per CTA whenever that keeps >= 3/4 of the SMs streaming: no cross-CTA fix-up in the tail, and
+        // (measured, profiles/r01_findings.md §7) grids of <= 16 CTAs per GPC finish together while 144-148 CTAs skew
+        // by 25 % because the 18/20-SM GPCs share the same GPC bandwidth as the 16-SM ones.
+        if (tile <= num_sms && tile * 4 >= num_sms * 3) g.grid = tile;
+        else if (tile > num_sms)
+            for (int cand = num_sms; cand * 4 >= num_sms * 3; --cand)
+                if (tile % cand == 0) { g.grid = cand; break; }
+    } else if (tile <= num_sms && tile * 10 >= num_sms * 9) g.grid = tile;
     const int per_cta = std::max(1, blk / g.grid);
     g.p.max_contrib = cdiv(kbmax, per_cta) + 1;
     g.p.counters = (unsigned*)dalloc((size_t)tile * 4, true);
@@ -525,11 +555,23 @@ void b200rwkv_engine::launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, siz
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (launch_cluster > 0) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = (unsigned)launch_cluster;
+        at[na].val.clusterDim.y = 1;
+        at[na].val.clusterDim.z = 1;
+        ++na;
+        launch_cluster = 0;
+    }
+    if (use_pdl && !prof) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = (use_pdl && !prof) ? 1 : 0;
+    cfg.numAttrs = na;
     cudaEvent_t ea = nullptr, eb = nullptr;
     if (prof) {
         CK(cudaEventCreate(&ea));
@@ -547,7 +589,8 @@ void b200rwkv_engine::launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, siz
 void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof) {
     switch (MT) {
         case 1:
-            if (gemm_half) launch_k(gemm_kernel<1, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, true>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            if (gemm_ring == 1) launch_k(gemm_kernel<1, 1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            else if (gemm_ring == 2) launch_k(gemm_kernel<1, 2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             else launch_k(gemm_kernel<1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             break;
         case 2: launch_k(gemm_kernel<2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<2>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
@@ -584,9 +627,14 @@ void b200rwkv_engine::build(const StFile& st) {
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&sm_stream, cudaStreamNonBlocking));
     CK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, true>::SMEM_BYTES));
-    if (const char* v = getenv("B200RWKV_GEMM_HALF")) gemm_half = atoi(v) != 0;
+    CK(cudaFuncSetAttribute(gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 1>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 2>::SMEM_BYTES));
+    if (const char* v = getenv("B200RWKV_GEMM_HALF")) gemm_ring = atoi(v) != 0 ? 1 : 0;
+    if (const char* v = getenv("B200RWKV_GEMM_RING")) gemm_ring = atoi(v);
+    if (const char* v = getenv("B200RWKV_PREFETCH_BLOCKS")) prefetch_blocks = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_LORA_CC")) lora_cc = atoi(v) != 0;
+    if (const char* v = getenv("B200RWKV_FUSED_PRE")) fused_pre = atoi(v) != 0;
+    if (const char* v = getenv("B200RWKV_LN_CLUSTER")) ln_cluster = atoi(v) != 0;
     CK(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<4>::SMEM_BYTES));
 
@@ -641,6 +689,9 @@ void b200rwkv_engine::build(const StFile& st) {
         f_rr = (float*)(comm_base + off_rr);
         d_logits = (float*)(comm_base + off_logits);
         d_epoch = (unsigned*)dalloc(16, true);
+        pre_gbar = (unsigned*)dalloc(16, true);
+        if (getenv("B200RWKV_STEP_TRACE")) d_step_trace = (unsigned long long*)dalloc((size_t)STEP_TRACE_MAX * STEP_TRACE_ROW * 8, true);
+        ln_cluster_ok = ln_cluster && C % (4 * PRE_CLUSTER) == 0 && C / (4 * PRE_CLUSTER) <= PRE_THREADS;
     }
     const int S_att = pick_split(Cl, cdiv(C, GEMM_BN)), S_ffn = pick_split(Fl, cdiv(C, GEMM_BN));
     split_att = S_att; split_ffn = S_ffn;
@@ -755,6 +806,17 @@ void b200rwkv_engine::build(const StFile& st) {
                     sv.push_back(d);
                 }
                 ly.pre.push_back(make_launch(sv));
+            }
+            if (fused_pre && (Dm == 32 || Dm == 64) && C % 128 == 0 && C <= PRE_MAX_C) {
+                auto upload_raw = [&](const StTensor& t) {
+                    __half* d = (__half*)dalloc(t.nbytes, false);
+                    CK(cudaMemcpy(d, t.data, t.nbytes, cudaMemcpyHostToDevice));
+                    return d;
+                };
+                ly.w1_raw = upload_raw(st.get(a + "time_mix_w1"));
+                ly.w2_raw = upload_raw(st.get(a + "time_mix_w2"));
+                for (int i = 0; i < 5; ++i) ly.mu5[i] = ly.pre[1].p.seg[i].aux2;
+                fused_pre_ok = true;
             }
             // R,K,V,G (column parallel by head) + decay LoRA stage 1 (replicated)
             {
@@ -1138,17 +1200,81 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
     const int rows = MT * 16;
     const int sk = skip_mask;
     auto big = [](const GemmLaunch& g) { return g.weight_bytes >= (8u << 20); };
+    auto gemm_skipped = [&](const GemmLaunch& g) { return big(g) ? (sk & 8) != 0 : (sk & 2) != 0; };
+    auto pre_skipped = [&](const Layer& ly, int gi) {
+        if (fold_wd2 && gi == ly.wd2_index) return true;
+        return fused_pre_ok && MT == 1 && ly.w1_raw && gi < 2;
+    };
+    // projection launches of this step in stream order: each one prefetches the head of the next into L2 (the last one
+    // wraps around to the first launch of the next step)
+    std::vector<const GemmLaunch*> seq;
+    if (prefetch_blocks > 0 && !(lora_cc && MT == 1)) {
+        for (int l = 0; l < L; ++l) {
+            const Layer& ly = layers[l];
+            for (int gi = 0; gi < (int)ly.pre.size(); ++gi)
+                if (!pre_skipped(ly, gi) && !gemm_skipped(ly.pre[gi])) seq.push_back(&ly.pre[gi]);
+            if (!gemm_skipped(ly.o)) seq.push_back(&ly.o);
+            for (auto& g : ly.ffn)
+                if (!gemm_skipped(g)) seq.push_back(&g);
+        }
+        if (MTR > 0 && !(sk & 16)) seq.push_back(&head);
+    }
+    size_t seq_pos = 0;
+    auto launch_gemm_chained = [&](const GemmLaunch& g, int mt) {
+        GemmLaunch g2 = g;
+        if (d_step_trace) g2.p.trace = tr_next(1000000 + (int)(g.weight_bytes >> 20));
+        if (!seq.empty()) {
+            REQUIRE(seq_pos < seq.size() && seq[seq_pos] == &g, B200RWKV_ERR_INVALID, "internal: projection launch order");
+            const GemmLaunch& nx = *seq[(seq_pos + 1) % seq.size()];
+            ++seq_pos;
+            g2.p.next_W = nx.p.W;
+            g2.p.next_blocks = nx.p.total_blocks;
+            g2.p.next_grid = nx.grid;
+            g2.p.prefetch_blocks = prefetch_blocks;
+        }
+        launch_gemm(g2, mt, s, prof);
+    };
     auto gemm = [&](const GemmLaunch& g) {
-        if (big(g) ? (sk & 8) : (sk & 2)) return;
-        launch_gemm(g, MT, s, prof);
+        if (gemm_skipped(g)) return;
+        launch_gemm_chained(g, MT);
     };
     if (!(sk & 1)) launch_k(embed_ln0_kernel, dim3(rows), dim3(LN_THREADS), 0, embed, KC_LN, s, prof);
+    auto launch_ln = [&](const LnMixParams& lp0) {
+        if (sk & 1) return;
+        LnMixParams lp = lp0;
+        lp.trace = tr_next(0);
+        if (ln_cluster_ok && MT == 1) {
+            launch_cluster = PRE_CLUSTER;
+            launch_k(ln_mix_cluster_kernel, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
+        } else {
+            launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, lp, KC_LN, s, prof);
+        }
+    };
     const int wkv_slots = std::min(S, rows);
     for (int l = 0; l < L; ++l) {
         Layer& ly = layers[l];
-        if (!(sk & 1)) launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, ly.ln1, KC_LN, s, prof);
+        const bool fused = fused_pre_ok && MT == 1 && ly.w1_raw;
+        if (fused) {
+            // LN1 + token shift + ddlerp LoRA (W1, tanh, W2, lerps) in one launch
+            if (!(sk & 1)) {
+                Pre6Params q;
+                memset(&q, 0, sizeof(q));
+                q.ln = ly.ln1;
+                q.ln.trace = tr_next(6);
+                q.W1 = ly.w1_raw; q.W2 = ly.w2_raw;
+                for (int j = 0; j < 5; ++j) { q.mu[j] = ly.mu5[j]; q.out[j] = a_x[j].p; }
+                q.lora = a_lora[0].p; q.lora_stride = (int)a_lora[0].halves_per_matrix;
+                q.Dm = info.time_mix_adapter;
+                q.gbar = pre_gbar;
+                launch_cluster = PRE_CLUSTER;
+                if (q.Dm == 32) launch_k(pre6_kernel<2>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+                else launch_k(pre6_kernel<4>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+            }
+        } else {
+            launch_ln(ly.ln1);
+        }
         for (int gi = 0; gi < (int)ly.pre.size(); ++gi) {
-            if (fold_wd2 && gi == ly.wd2_index) continue;
+            if (pre_skipped(ly, gi)) continue;
             if (lora_cc && MT == 1 && l < (int)mega_smallns.size() && gi == 0) {
                 if (!(sk & 2)) launch_k(smalln_kernel, dim3(std::min(num_sms, mega_smallns[l].N)), dim3(CONSUMER_THREADS), 0, mega_smallns[l], KC_OTHER, s, prof);
                 continue;
@@ -1160,19 +1286,23 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             gemm(ly.pre[gi]);
         }
         const size_t wkv_smem = fold_wd2 ? wkv_fold_smem_bytes(info.time_decay_adapter, maxT) : 0;
-        if (!(sk & 4)) switch (info.version) {
-            case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof, maxT); break;
-            case 6: launch_k(wkv_kernel<6>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), wkv_smem, ly.wkv, KC_WKV, s, prof, maxT); break;
-            default: launch_k(wkv_kernel<7>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, ly.wkv, KC_WKV, s, prof, maxT); break;
+        if (!(sk & 4)) {
+            WkvParams wp = ly.wkv;
+            wp.trace = tr_next(2);
+            switch (info.version) {
+                case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, wp, KC_WKV, s, prof, maxT); break;
+                case 6: launch_k(wkv_kernel<6>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), wkv_smem, wp, KC_WKV, s, prof, maxT); break;
+                default: launch_k(wkv_kernel<7>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, wp, KC_WKV, s, prof, maxT); break;
+            }
         }
         gemm(ly.o);
         if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
-        if (!(sk & 1)) launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, ly.ln2, KC_LN, s, prof);
+        launch_ln(ly.ln2);
         for (auto& g : ly.ffn) gemm(g);
         if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
     }
     if (!(sk & 1)) launch_k(ln_out_kernel, dim3(rows), dim3(LN_THREADS), 0, lnout, KC_LN, s, prof);
-    if (MTR > 0 && !(sk & 16)) launch_gemm(head, MTR, s, prof);
+    if (MTR > 0 && !(sk & 16)) launch_gemm_chained(head, MTR);
     if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
 }
 
@@ -1787,6 +1917,18 @@ int32_t b200rwkv_debug_read(b200rwkv_engine* e, const char* name, float* out, si
 // B200RWKV_TRACE=1 at creation).  out: [4][nphase][2] u64; types: [nphase] phase types.
 int32_t b200rwkv_debug_trace(b200rwkv_engine* e, uint64_t* out, size_t cap, int32_t* types, int32_t* nphase) {
     if (!e || !out || !types || !nphase) return B200RWKV_ERR_INVALID;
+    if (e->d_step_trace && !(e->mega_ok && e->mega.trace)) {
+        // per-op chain: one row of 8 stamps per launch of the last captured step shape
+        const size_t nl = e->step_trace_types.size();
+        const size_t row = b200rwkv_engine::STEP_TRACE_ROW;
+        if (cap < nl * row) return B200RWKV_ERR_INVALID;
+        cudaSetDevice(e->dev);
+        cudaStreamSynchronize(e->stream);
+        if (cudaMemcpy(out, e->d_step_trace, nl * row * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return B200RWKV_ERR_CUDA;
+        for (size_t i = 0; i < nl; ++i) types[i] = e->step_trace_types[i];
+        *nphase = (int32_t)nl;
+        return B200RWKV_OK;
+    }
     if (!e->mega_ok || !e->mega.trace) { e->err = "no trace (set B200RWKV_TRACE=1)"; return B200RWKV_ERR_INVALID; }
     const size_t n = (size_t)4 * e->mega.nphase * 12;
     if (cap < n) return B200RWKV_ERR_INVALID;

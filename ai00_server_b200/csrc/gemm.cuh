@@ -86,16 +86,24 @@ struct GemmParams {
     const int* nrows;       // device: valid token rows
     uint32_t w_lbo, w_sbo, a_lbo, a_sbo;   // UMMA descriptor strides (bytes)
     unsigned long long* trace;             // profiling aid: 8 globaltimer stamps of CTA 0 (null in production)
+    // L2 prefetch of the NEXT projection launch of the step (set per launch by the engine): when this CTA's producer
+    // has requested its last block it asks L2 for the first `prefetch_blocks` blocks the same CTA index will stream in
+    // that launch, so HBM keeps working through this launch's tail, the launch boundary and any small kernel between
+    const uint8_t* next_W;
+    int next_blocks, next_grid, prefetch_blocks;
     GemmSeg seg[GEMM_MAX_SEG];
 };
 
 // HALF: ring sized to half an SM's shared memory, so the NEXT projection launch (programmatic
 // dependent launch) can be resident and prefetching its first weight blocks while this one drains
-template <int MT, bool HALF = false>
+// RING 0: as many stages as fit an SM; 1: half of that (two projection CTAs per SM); 2: one stage less than 0, which
+// leaves ~40 KB of shared memory so the small kernels around a projection (pre6 / LN / WKV) can share its SMs
+template <int MT, int RING = 0>
 struct GemmCfg {
     static constexpr int STAGE_BYTES = GEMM_WBYTES + MT * GEMM_ABYTES;
-    static constexpr int BUDGET = HALF ? (GEMM_SMEM_BUDGET / 2) : GEMM_SMEM_BUDGET;
-    static constexpr int NSTAGE = (BUDGET / STAGE_BYTES) > 12 ? 12 : (BUDGET / STAGE_BYTES);
+    static constexpr int BUDGET = RING == 1 ? (GEMM_SMEM_BUDGET / 2) : GEMM_SMEM_BUDGET;
+    static constexpr int NFIT = (BUDGET / STAGE_BYTES) > 12 ? 12 : (BUDGET / STAGE_BYTES);
+    static constexpr int NSTAGE = (RING == 2 && NFIT > 2) ? NFIT - 1 : NFIT;
     static constexpr int BAR_BYTES = (2 * NSTAGE + 4) * 8 + 16;
     static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + BAR_BYTES + 64;
     static constexpr int TMEM_COLS = (2 * 16 * MT) < 32 ? 32 : (2 * 16 * MT);   // double-buffered accumulator
@@ -339,9 +347,9 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
 // ---------------------------------------------------------------------------------------
 // stand-alone kernel: warps 0-3 epilogue, warp 4 MMA issuer (+ TMEM allocation), warp 5 TMA producer
 // ---------------------------------------------------------------------------------------
-template <int MT, bool HALF = false>
-__global__ void __launch_bounds__(GEMM_THREADS, HALF ? 2 : 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<MT, HALF>;
+template <int MT, int RING = 0>
+__global__ void __launch_bounds__(GEMM_THREADS, RING == 1 ? 2 : 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<MT, RING>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int s_last;
     const uint32_t smem_base = smem_u32(smem);
@@ -428,6 +436,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, HALF ? 2 : 1) gemm_kernel(const 
                     blocks_left_in_seg = sg->tiles * sg->KB;
                 }
             }
+            if (p.next_W && cta < p.next_grid) {
+                const int n0 = (int)((long long)cta * p.next_blocks / p.next_grid);
+                const int n1 = (int)((long long)(cta + 1) * p.next_blocks / p.next_grid);
+                const int np = min(n1 - n0, p.prefetch_blocks);
+                for (int i = 0; i < np; ++i) bulk_prefetch_l2(p.next_W + (size_t)(n0 + i) * GEMM_WBYTES, GEMM_WBYTES);
+            }
         }
     } else if (warp == GEMM_EPI_WARPS) {
         // ===================== MMA issuer: one lane =====================
@@ -438,6 +452,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, HALF ? 2 : 1) gemm_kernel(const 
             gemm_mma_role<MT, Cfg::NSTAGE, Cfg::STAGE_BYTES>(p, b0, b1, smem_base, full_bar, empty_bar, tfull_bar, tempty_bar,
                                                              tmem_base, rp, segcount);
             stamp(4);
+            if (p.trace) {       // every CTA: SM id and the time its last MMA was issued (skew across the grid)
+                unsigned smid;
+                asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+                p.trace[8 + 3 * cta] = smid;
+                p.trace[8 + 3 * cta + 1] = globaltimer_ns();
+            }
         }
     } else {
         // ===================== epilogue: 4 warps =====================
@@ -450,6 +470,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, HALF ? 2 : 1) gemm_kernel(const 
     tc_fence_before();
     __syncthreads();
     if (tid == 0) stamp(7);
+    if (tid == 0 && p.trace) p.trace[8 + 3 * cta + 2] = globaltimer_ns();
     if (warp == GEMM_EPI_WARPS) tc_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 

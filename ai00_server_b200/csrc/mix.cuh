@@ -45,6 +45,7 @@ struct LnMixParams {
     float* sx_out;          // [T, C] or null
     float* commit_dst;      // [S, C] or null
     const float* commit_src;    // [T, C]
+    unsigned long long* trace;  // profiling aid (null in production)
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -228,11 +229,14 @@ __device__ __forceinline__ void ln_mix_row(const LnMixParams& p, const int t, fl
 
 __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const __grid_constant__ LnMixParams p) {
     __shared__ float red[32];
+    trace_stamp(p.trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    trace_stamp(p.trace, 1);
     const int t = blockIdx.x;
     if (t >= p.meta.T()) return;
     ln_mix_row<false>(p, t, red);
+    trace_stamp(p.trace, 7);
 }
 
 // ---------------------------------------------------------------------------------------

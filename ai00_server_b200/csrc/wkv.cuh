@@ -63,6 +63,7 @@ struct WkvParams {
     const __half* d1;       // A16 [T, Dd]: tanh(time_decay_w1 @ xw)
     int d1_kq;
     int Dd;
+    unsigned long long* trace;  // profiling aid (null in production)
 };
 
 struct WkvShared {
@@ -214,6 +215,7 @@ template <int VER>
 __global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant__ WkvParams p, const int max_tokens) {
     __shared__ WkvShared sm;
     extern __shared__ __align__(16) uint8_t wkv_dyn[];
+    trace_stamp(p.trace, 0);
     pdl_launch_dependents();
     const int si = blockIdx.y;
     const int h = blockIdx.x;
@@ -228,6 +230,7 @@ __global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant_
         for (int i = tid; i < WKV_N * p.Dd / 8; i += WKV_THREADS) dst[i] = src[i];
     }
     pdl_wait();
+    trace_stamp(p.trace, 1);
     if (si >= p.meta.nslots()) return;
     const int slot = p.meta.slot_id()[si];
     const int t0 = p.meta.slot_start()[si];
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant_
     wkv_slot<VER, false>(p, h, t0, nt, m, sm, w_local, 0);
 #pragma unroll
     for (int e = 0; e < 4; ++e) __stcs(reinterpret_cast<float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4), m[e]);
+    trace_stamp(p.trace, 7);
 }
 
 }  // namespace b200

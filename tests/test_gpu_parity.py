@@ -240,8 +240,8 @@ def test_wkv_kernels_reproduce_fla_fixtures(models, golden_dir):
 @pytest.mark.parametrize("preset", ["tiny5", "tiny6", "tiny7"])
 def test_whole_step_kernel_equals_per_op_kernels(models, preset):
     """The persistent whole-step kernel (decode, <= 16 tokens) and the per-op kernel chain share
-    their device functions: same logits and state (bit-identical for v5/v7; v6 evaluates the
-    decay LoRA stage 2 in a different summation order)."""
+    the WKV / projection device functions: same logits and state up to summation order (the per-op chain
+    computes LN statistics per cluster, the whole-step kernel per CTA)."""
     a, orc, _ = models(preset, mega=True)
     b, _, _ = models(preset, mega=False)
     assert a is not b
@@ -257,12 +257,11 @@ def test_whole_step_kernel_equals_per_op_kernels(models, preset):
             rows = m.infer_raw([0, 1, 2, 3], [1] * 4, [7, 8, 9, 10], [capi.OPTION_LAST] * 4)
         outs.append((np.concatenate(rows), [m.state.back(s) for s in range(4)]))
     (la, sa), (lb, sb) = outs
-    if preset == "tiny6":
-        assert rel_err(la, lb) <= 5e-4
-    else:
-        assert np.array_equal(la, lb)
-        for x, y in zip(sa, sb):
-            assert np.array_equal(x, y)
+    # the two paths reduce LN statistics / LoRA stages in different (deterministic) orders: close, not bit-identical
+    assert rel_err(la, lb) <= REL_TOL
+    assert (la.argmax(1) == lb.argmax(1)).all()
+    for x, y in zip(sa, sb):
+        assert rel_err(x, y) <= REL_TOL
     want = [orc.run(r + [7], st) for r in runs]     # sanity vs the oracle on the first decode step only
     assert la.shape == lb.shape
 
@@ -312,7 +311,9 @@ def test_tensor_parallel_two_ranks_in_process(preset):
         m.close()
 
 
-@pytest.mark.parametrize("env", [{"B200RWKV_LORA_CC": "1"}, {"B200RWKV_GEMM_HALF": "1"}, {"B200RWKV_NOFOLD": "1", "B200RWKV_NOSPLIT": "1"}])
+@pytest.mark.parametrize("env", [{"B200RWKV_LORA_CC": "1", "B200RWKV_FUSED_PRE": "0"}, {"B200RWKV_GEMM_HALF": "1"},
+                                 {"B200RWKV_NOFOLD": "1", "B200RWKV_NOSPLIT": "1"},
+                                 {"B200RWKV_FUSED_PRE": "0", "B200RWKV_LN_CLUSTER": "0"}, {"B200RWKV_FUSED_PRE": "0"}])
 def test_kernel_variants_match_oracle(models, env):
     """Alternative kernel choices of the per-op chain (CUDA-core LoRA kernels, half-ring GEMM, un-folded decay
     LoRA / stream-K fix-up instead of split-K) compute the same model."""
@@ -327,3 +328,24 @@ def test_kernel_variants_match_oracle(models, env):
         for s in range(3):
             want, sts[s] = orc.run([int(toks[i, s])], sts[s])
             assert rel_err(rows[s], want) <= REL_TOL and rows[s].argmax() == want.argmax()
+
+
+@pytest.mark.parametrize("preset", ["small6", "tiny7", "tiny5"])
+def test_short_ragged_steps_use_the_cluster_kernels(models, preset):
+    """<= 16 tokens in a step with several tokens per slot: the decode-shaped cluster kernels (pre6.cuh) recompute the
+    previous token's LN output instead of reading the shift state."""
+    m, orc, _ = models(preset, mega=False)
+    rng = np.random.default_rng(21)
+    counts = [3, 1, 5]
+    sts = [orc.state_init() for _ in counts]
+    for s in range(len(counts)):
+        m.state.load(m.state.init(), s)
+    for _ in range(3):
+        toks = [rng.integers(1, 500, size=n).tolist() for n in counts]
+        rows = m.infer_raw([0, 1, 2], counts, sum(toks, []), [capi.OPTION_LAST] * 3)
+        for s in range(3):
+            want, sts[s] = orc.run(toks[s], sts[s])
+            assert rel_err(rows[s], want) <= REL_TOL and rows[s].argmax() == want.argmax()
+    for s in range(3):
+        got = m.state.back(s)
+        assert rel_err(got, sts[s]) <= 5 * REL_TOL
