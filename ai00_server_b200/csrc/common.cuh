@@ -160,6 +160,10 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// fire-and-forget arrival: no value comes back, so the arriving thread pays a one-way trip
+__device__ __forceinline__ void red_add_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -689,7 +689,7 @@ void b200rwkv_engine::build(const StFile& st) {
         f_rr = (float*)(comm_base + off_rr);
         d_logits = (float*)(comm_base + off_logits);
         d_epoch = (unsigned*)dalloc(16, true);
-        pre_gbar = (unsigned*)dalloc(16, true);
+        pre_gbar = (unsigned*)dalloc(256, true);
         if (getenv("B200RWKV_STEP_TRACE")) d_step_trace = (unsigned long long*)dalloc((size_t)STEP_TRACE_MAX * STEP_TRACE_ROW * 8, true);
         ln_cluster_ok = ln_cluster && C % (4 * PRE_CLUSTER) == 0 && C / (4 * PRE_CLUSTER) <= PRE_THREADS;
     }
@@ -1285,14 +1285,15 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             }
             gemm(ly.pre[gi]);
         }
-        const size_t wkv_smem = fold_wd2 ? wkv_fold_smem_bytes(info.time_decay_adapter, maxT) : 0;
         if (!(sk & 4)) {
+            // decays / staged rows are sized by the step shape: a slot cannot hold more tokens than the step
+            const size_t wkv_smem = wkv_smem_bytes(info.version, fold_wd2, info.time_decay_adapter, rows);
             WkvParams wp = ly.wkv;
             wp.trace = tr_next(2);
             switch (info.version) {
-                case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, wp, KC_WKV, s, prof, maxT); break;
-                case 6: launch_k(wkv_kernel<6>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), wkv_smem, wp, KC_WKV, s, prof, maxT); break;
-                default: launch_k(wkv_kernel<7>, dim3(Hl, wkv_slots), dim3(WKV_THREADS), 0, wp, KC_WKV, s, prof, maxT); break;
+                case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), wkv_smem, wp, KC_WKV, s, prof, rows); break;
+                case 6: launch_k(wkv_kernel<6>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), wkv_smem, wp, KC_WKV, s, prof, rows); break;
+                default: launch_k(wkv_kernel<7>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), wkv_smem, wp, KC_WKV, s, prof, rows); break;
             }
         }
         gemm(ly.o);

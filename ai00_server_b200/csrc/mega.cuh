@@ -329,7 +329,7 @@ __device__ void mega_wkv_phase(const MegaParams& mp, const WkvParams& w, const i
                 m[e] = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), __uint_as_float(raw.w));
             }
             ring_release(empty_bar, rp);            // the patch is in registers: free the slot early
-            wkv_slot<VER, true>(w, h, t0, nt, m, sh.wkv, VER == 6 ? sh.w_s : nullptr, lt0, sh.pre, MEGA_MAX_TOK * WKV_N);
+            wkv_slot<VER, true>(w, h, t0, nt, reinterpret_cast<float (&)[4][4]>(m), sh.wkv, VER == 6 ? sh.w_s : nullptr, lt0, sh.pre, MEGA_MAX_TOK * WKV_N);
             float* M = w.state + ((size_t)slot * w.H + h) * (WKV_N * WKV_N);
 #pragma unroll
             for (int e = 0; e < 4; ++e) __stcs(reinterpret_cast<float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4), m[e]);

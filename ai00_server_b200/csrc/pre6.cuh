@@ -46,7 +46,7 @@ struct Pre6Params {
     int lora_stride;          // halves between them
     __half* out[5];           // A16 [16][C] operands of decay-LoRA, K, V, R, G
     int Dm;
-    unsigned* gbar;           // {count, generation}
+    unsigned* gbar;           // two arrival counters, 128 bytes apart
 };
 
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
@@ -56,19 +56,23 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// grid barrier of the 16 clusters: hardware cluster barrier, one global arrival per cluster, cluster barrier again
-__device__ __forceinline__ void pre_grid_barrier(cg::cluster_group& cl, const unsigned rank, unsigned* gbar, const unsigned tag) {
+// Grid barrier of the 16 clusters: hardware cluster barrier, one fire-and-forget arrival per cluster on `mine`, spin
+// until all 16 arrived, cluster barrier again.  The two barriers of a launch use two counters and CTA 0 re-arms them
+// where no arrival can race with the reset:
+//   `reset_before` (barrier 1 re-arms counter 2): its last use was the previous launch, and the store is ordered
+//       before CTA 0's own release-arrival, which every cluster acquires before it can reach barrier 2;
+//   `reset_after`  (barrier 2 re-arms counter 1): everybody arrived at barrier 2, so nobody still polls counter 1, and
+//       its next arrivals belong to the next launch.
+__device__ __forceinline__ void pre_grid_barrier(cg::cluster_group& cl, const unsigned rank, unsigned* mine, unsigned* reset_before,
+                                                 unsigned* reset_after, const unsigned tag) {
     cl.sync();
     if (rank == 0 && threadIdx.x == 0) {
-        const unsigned gen = ld_relaxed_gpu(gbar + 1);      // cannot advance before this cluster arrives
-        const unsigned old = atom_add_acq_rel_gpu(gbar, 1u);
-        if (old == (unsigned)(PRE_NCLUSTER - 1)) {
-            st_relaxed_gpu(gbar, 0u);
-            st_release_gpu(gbar + 1, gen + 1);
-        } else {
-            SpinGuard sg_;
-            while (ld_acquire_gpu(gbar + 1) == gen) sg_.poll(WD_GRIDBAR, 0x600u + tag, gen, old);
-        }
+        if (blockIdx.x == 0 && reset_before) st_relaxed_gpu(reset_before, 0u);
+        red_add_release_gpu(mine, 1u);
+        SpinGuard sg_;
+        unsigned seen;
+        while ((seen = ld_acquire_gpu(mine)) < (unsigned)PRE_NCLUSTER) sg_.poll(WD_GRIDBAR, 0x600u + tag, seen, blockIdx.x);
+        if (blockIdx.x == 0 && reset_after) st_relaxed_gpu(reset_after, 0u);
         __threadfence();
     }
     cl.sync();
@@ -109,17 +113,38 @@ __device__ __forceinline__ float4 residual_vec(const ResidualSrc& r, const int t
     return a;
 }
 
+// LN statistics of a row spread over the cluster: each CTA reduces its slice to (mean_i, M2_i) and ONE exchange through
+// distributed shared memory combines them (Chan et al.): mean = avg mean_i, M2 = sum M2_i + n_i sum (mean_i - mean)^2.
+// `xch` must be a buffer no earlier exchange of this launch used (a fast CTA may write the next exchange while a slow
+// one still reads this one).
 __device__ __forceinline__ void slice_stats(cg::cluster_group& cl, const unsigned rank, const int C, const bool act, const float4 a,
-                                            float* red, float* xch0, float* xch1, float& mean, float& rstd) {
+                                            float* red, float* xch, float& mean, float& rstd) {
+    const int Cs = C / PRE_CLUSTER;
     const float s = act ? (a.x + a.y) + (a.z + a.w) : 0.f;
-    mean = cluster_sum(cl, rank, xch0, block_sum<false>(s, red)) / (float)C;
+    const float mi = block_sum<false>(s, red) / (float)Cs;
     float s2 = 0.f;
     if (act) {
-        const float dx = a.x - mean, dy = a.y - mean, dz = a.z - mean, dw = a.w - mean;
+        const float dx = a.x - mi, dy = a.y - mi, dz = a.z - mi, dw = a.w - mi;
         s2 = (dx * dx + dy * dy) + (dz * dz + dw * dw);
     }
-    const float var = cluster_sum(cl, rank, xch1, block_sum<false>(s2, red)) / (float)C;
-    rstd = 1.0f / sqrtf(var + LN_EPS);
+    const float m2i = block_sum<false>(s2, red);
+    if (threadIdx.x < PRE_CLUSTER) {
+        float* dst = cl.map_shared_rank(xch, threadIdx.x);
+        dst[rank] = mi;
+        dst[PRE_CLUSTER + rank] = m2i;
+    }
+    cl.sync();
+    float ms = 0.f;
+#pragma unroll
+    for (int i = 0; i < PRE_CLUSTER; ++i) ms += xch[i];      // fixed order: identical in all CTAs
+    mean = ms / (float)PRE_CLUSTER;
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PRE_CLUSTER; ++i) {
+        const float d = xch[i] - mean;
+        m2 += xch[PRE_CLUSTER + i] + (float)Cs * d * d;
+    }
+    rstd = 1.0f / sqrtf(m2 / (float)C + LN_EPS);
 }
 
 template <int NMIX>
@@ -150,7 +175,7 @@ __device__ __forceinline__ PreLnStatic<NMIX> pre_ln_static(const LnMixParams& p,
 // phase 1 for token t, channel slice `rank` (thread owns channels rank*C/8 + 4*tid .. +3)
 template <int NMIX>
 __device__ __forceinline__ void pre_ln_slice(const LnMixParams& p, const int t, cg::cluster_group& cl, const unsigned rank,
-                                             const PreLnStatic<NMIX>& st, float* red, float (*xch)[PRE_CLUSTER]) {
+                                             const PreLnStatic<NMIX>& st, float* red, float (*xch)[2 * PRE_CLUSTER]) {
     const int C = p.C, Cs = C / PRE_CLUSTER;
     const bool act = 4 * (int)threadIdx.x < Cs;
     const int c = act ? (int)rank * Cs + 4 * (int)threadIdx.x : 0;
@@ -166,11 +191,11 @@ __device__ __forceinline__ void pre_ln_slice(const LnMixParams& p, const int t, 
     float4 a = act ? residual_vec(r, t, c) : z4;
     if (act && (p.x_out != p.x_in || p.n_parts > 0)) *reinterpret_cast<float4*>(p.x_out + (size_t)t * C + c) = a;
     float mean, rstd;
-    slice_stats(cl, rank, C, act, a, red, xch[0], xch[1], mean, rstd);
+    slice_stats(cl, rank, C, act, a, red, xch[0], mean, rstd);
     if (prev_t >= 0) {          // multi-token slot: previous token's LN output, recomputed (uniform over the cluster)
         float pmean, prstd;
         pv = act ? residual_vec(r, prev_t, c) : z4;
-        slice_stats(cl, rank, C, act, pv, red, xch[2], xch[3], pmean, prstd);
+        slice_stats(cl, rank, C, act, pv, red, xch[1], pmean, prstd);
         pv = ln_apply(pv, pmean, prstd, st.w, st.b);
     }
     if (!act) return;
@@ -195,7 +220,7 @@ __device__ __forceinline__ void pre_ln_slice(const LnMixParams& p, const int t, 
 // LN stage alone (channel mix of every version, time mix of RWKV-5/7): 16 clusters x 8, no grid barrier
 __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __grid_constant__ LnMixParams p) {
     __shared__ float red[32];
-    __shared__ float xch[4][PRE_CLUSTER];
+    __shared__ float xch[2][2 * PRE_CLUSTER];
     cg::cluster_group cl = cg::this_cluster();
     const unsigned rank = cl.block_rank();
     const int t = blockIdx.x / PRE_CLUSTER;
@@ -214,7 +239,7 @@ __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __gri
 template <int KD>
 __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_constant__ Pre6Params p) {
     __shared__ float red[32];
-    __shared__ float xch[4][PRE_CLUSTER];
+    __shared__ float xch[2][2 * PRE_CLUSTER];
     __shared__ __align__(16) float red2[8][PRE_NT2 * 4 * 32];
     __shared__ float part[PRE_NT2 * 4 * 32];
     cg::cluster_group cl = cg::this_cluster();
@@ -228,6 +253,10 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
     const int C = p.ln.C, Cs = C / PRE_CLUSTER;
     unsigned long long* const tr = p.ln.trace;
     trace_stamp(tr, 0);
+    auto cta_stamp = [&](int i) {       // profiling aid: every CTA's {entry, wait released, phase 1 done} for skew analysis
+        if (tr && threadIdx.x == 0) tr[8 + 3 * blockIdx.x + i] = globaltimer_ns();
+    };
+    cta_stamp(0);
     pdl_launch_dependents();
 
     // ---------------- static operands (weights): in flight while the previous kernel drains ----------------
@@ -273,12 +302,14 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
     }
     pdl_wait();
     trace_stamp(tr, 1);
+    cta_stamp(1);
     const int T = min(st.T, 16);
 
     // ---------------- phase 1: token g ----------------
     if (g < T) pre_ln_slice(p.ln, g, cl, rank, st, red, xch);
     trace_stamp(tr, 2);
-    pre_grid_barrier(cl, rank, p.gbar, 1);
+    cta_stamp(2);
+    pre_grid_barrier(cl, rank, p.gbar, p.gbar + 32, nullptr, 1);
     trace_stamp(tr, 3);
 
     // ---------------- phase 2: tanh(W1 xxx), rows of cluster g, K slice `rank` ----------------
@@ -337,7 +368,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
         }
     }
     trace_stamp(tr, 4);
-    pre_grid_barrier(cl, rank, p.gbar, 2);      // also keeps every CTA alive until its peers finished reading `part`
+    pre_grid_barrier(cl, rank, p.gbar + 32, nullptr, p.gbar, 2);      // also keeps every CTA alive until its peers finished reading `part`
 
     trace_stamp(tr, 5);
     // ---------------- phase 3: x_j = xx + sx * (mu_j + W2_j tanh_j) ----------------

@@ -77,18 +77,25 @@ struct WkvShared {
 // `pre`: optional shared-memory copy of the head's per-token vectors, [array][token][64] with arrays
 // r, k, v, g (, w, a, nu for v7) and `pre_stride` floats between arrays (whole-step kernel: gathered
 // once per WKV unit so the per-token loop never waits on L2).
-template <int VER, bool MEGA>
-__device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const int t0, const int nt, float4 (&m)[4],
+// KC: key columns per thread (4: 256 threads per head, 8: 128 threads per head); the thread's patch is m[e][f] =
+// M[4*ig + e][KC*j4 + f].
+template <int VER, bool MEGA, int KC = 4>
+__device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const int t0, const int nt, float (&m)[4][KC],
                                          WkvShared& sm, const float* w_local, const int lt0, const float* pre = nullptr,
-                                         const int pre_stride = 0) {
+                                         const int pre_stride = 0, const float* statics = nullptr) {
+    // `statics`: optional shared-memory copy of this head's [ln_x weight 64][ln_x bias 64][time_first 64], staged by the
+    // caller before it waited on the producer kernel (keeps three L2 round trips off the per-step chain)
     const int tid = threadIdx.x;
-    const int ig = tid >> 4;           // value rows 4*ig .. 4*ig+3
-    const int j4 = tid & 15;           // key cols  4*j4 .. 4*j4+3
+    constexpr int LANES = WKV_N / KC;  // threads that share a value row (reduction width)
+    const int ig = tid / LANES;        // value rows 4*ig .. 4*ig+3
+    const int j4 = tid % LANES;        // key cols  KC*j4 .. KC*j4+KC-1
     const int ch = h * WKV_N;          // channel base of this head
-    float u4[4] = {0.f, 0.f, 0.f, 0.f};
+    float u4[KC];
+#pragma unroll
+    for (int f = 0; f < KC; ++f) u4[f] = 0.f;
     if (VER != 7) {
 #pragma unroll
-        for (int f = 0; f < 4; ++f) u4[f] = p.u[ch + j4 * 4 + f];
+        for (int f = 0; f < KC; ++f) u4[f] = statics ? statics[2 * WKV_N + j4 * KC + f] : p.u[ch + j4 * KC + f];
     }
     for (int tt = 0; tt < nt; ++tt) {
         const int t = t0 + tt;
@@ -125,18 +132,18 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
         }
         cta_sync<MEGA>();
 
-        float rr[4], kk_[4], ww[4];
+        float rr[KC], kk_[KC], ww[KC];
 #pragma unroll
-        for (int f = 0; f < 4; ++f) { rr[f] = sm.r[j4 * 4 + f]; kk_[f] = sm.k[j4 * 4 + f]; ww[f] = sm.w[j4 * 4 + f]; }
+        for (int f = 0; f < KC; ++f) { rr[f] = sm.r[j4 * KC + f]; kk_[f] = sm.k[j4 * KC + f]; ww[f] = sm.w[j4 * KC + f]; }
         float o[4];
         if (VER != 7) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float vv = sm.v[ig * 4 + e];
-                float* me = reinterpret_cast<float*>(&m[e]);
+                float* me = m[e];
                 float acc = 0.f;
 #pragma unroll
-                for (int f = 0; f < 4; ++f) {
+                for (int f = 0; f < KC; ++f) {
                     const float kv = kk_[f] * vv;
                     acc += rr[f] * (u4[f] * kv + me[f]);
                     me[f] = kv + ww[f] * me[f];
@@ -144,26 +151,29 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
                 o[e] = acc;
             }
         } else {
-            float nk[4], ka[4];
+            float nk[KC], ka[KC];
 #pragma unroll
-            for (int f = 0; f < 4; ++f) { nk[f] = sm.o[j4 * 4 + f]; ka[f] = sm.b[j4 * 4 + f]; }
+            for (int f = 0; f < KC; ++f) { nk[f] = sm.o[j4 * KC + f]; ka[f] = sm.b[j4 * KC + f]; }
             float sa[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float* me = reinterpret_cast<const float*>(&m[e]);
-                sa[e] = (me[0] * nk[0] + me[1] * nk[1]) + (me[2] * nk[2] + me[3] * nk[3]);
+                const float* me = m[e];
+                float s_ = 0.f;
+#pragma unroll
+                for (int f = 0; f < KC; f += 4) s_ += (me[f] * nk[f] + me[f + 1] * nk[f + 1]) + (me[f + 2] * nk[f + 2] + me[f + 3] * nk[f + 3]);
+                sa[e] = s_;
             }
 #pragma unroll
-            for (int off = 8; off > 0; off >>= 1)
+            for (int off = LANES / 2; off > 0; off >>= 1)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) sa[e] += __shfl_xor_sync(0xffffffffu, sa[e], off);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float vv = sm.v[ig * 4 + e];
-                float* me = reinterpret_cast<float*>(&m[e]);
+                float* me = m[e];
                 float acc = 0.f;
 #pragma unroll
-                for (int f = 0; f < 4; ++f) {
+                for (int f = 0; f < KC; ++f) {
                     me[f] = me[f] * ww[f] + sa[e] * ka[f] + vv * kk_[f];
                     acc += me[f] * rr[f];
                 }
@@ -171,7 +181,7 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
             }
         }
 #pragma unroll
-        for (int off = 8; off > 0; off >>= 1)
+        for (int off = LANES / 2; off > 0; off >>= 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], off);
         cta_sync<MEGA>();              // all reads of sm.o (-kk) done before it is overwritten
@@ -188,8 +198,11 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
             const float d0 = x0 - mean, d1 = x1 - mean;
             const float var = warp_sum(d0 * d0 + d1 * d1) * (1.f / WKV_N);
             const float rstd = 1.0f / sqrtf(var + GN_EPS);
-            float y0 = d0 * rstd * p.lnx_w[ch + tid] + p.lnx_b[ch + tid];
-            float y1 = d1 * rstd * p.lnx_w[ch + tid + 32] + p.lnx_b[ch + tid + 32];
+            const float lw0 = statics ? statics[tid] : p.lnx_w[ch + tid], lw1 = statics ? statics[tid + 32] : p.lnx_w[ch + tid + 32];
+            const float lb0 = statics ? statics[WKV_N + tid] : p.lnx_b[ch + tid];
+            const float lb1 = statics ? statics[WKV_N + tid + 32] : p.lnx_b[ch + tid + 32];
+            float y0 = d0 * rstd * lw0 + lb0;
+            float y1 = d1 * rstd * lw1 + lb1;
             if (VER == 7) {
                 const float bonus = sm.red[2] + sm.red[3];
                 y0 += bonus * sm.v[tid];
@@ -205,14 +218,32 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
     }
 }
 
-// dynamic shared memory of the stand-alone kernel when the v6 decay LoRA stage 2 is folded in:
-// [Dd][64] halves (k-major slice of time_decay_w2) | [max tokens][64] floats (decays) | [Dd] halves | [4][64] floats
-__host__ __device__ inline size_t wkv_fold_smem_bytes(int Dd, int max_tokens) {
-    return (size_t)WKV_N * Dd * 2 + (size_t)max_tokens * WKV_N * 4 + (size_t)Dd * 2 + 4 * WKV_N * 4 + 64;
+// Stand-alone kernel, one CTA of 128 threads per (head, slot); each thread owns a 4 x 8 patch of the state.
+// Shape: 64 heads x 16 slots = 1024 CTAs must be ONE wave (measured: with 256 threads x 64 registers only 592 fit and the
+// second wave doubled the kernel), i.e. <= 72 registers at 7 CTAs per SM with half of them holding state.
+// A decode step is a latency chain, not bandwidth (16 KB of state per CTA), so everything no kernel of this step writes --
+// the decay-LoRA slice, ln_x, time_first, the step metadata -- is staged BEFORE griddepcontrol.wait, and after it one
+// batch of loads brings the state patch, the head's r/k/v/g(/w/a/nu) rows of up to WKV_STAGE_TOK tokens and the
+// decay-LoRA inputs; longer slots (prefill chunks) read per token instead.
+constexpr int WKV_SA_THREADS = 128;
+constexpr int WKV_SA_KC = 8;
+constexpr int WKV_STAGE_TOK = 4;
+constexpr int WKV_STAGE_ARRAYS = 7;      // r, k, v, g, w, a, nu
+
+__host__ __device__ inline int wkv_stage_arrays(int ver, bool fold) { return ver == 7 ? 7 : ((ver == 6 && !fold) ? 5 : 4); }
+
+// dynamic shared memory: [fold only: [Dd][64] halves (k-major slice of time_decay_w2) | [max tokens][64] floats (decays) |
+// [WKV_STAGE_TOK][Dd] halves | [2][64] floats] | staged rows [arrays][WKV_STAGE_TOK][64] floats | statics [3][64] floats
+__host__ __device__ inline size_t wkv_smem_bytes(int ver, bool fold, int Dd, int max_tokens) {
+    size_t b = 0;
+    if (fold) b += (size_t)WKV_N * Dd * 2 + (size_t)max_tokens * WKV_N * 4 + ((((size_t)WKV_STAGE_TOK * Dd * 2) + 15) & ~(size_t)15) + 2 * WKV_N * 4;
+    b += (size_t)wkv_stage_arrays(ver, fold) * WKV_STAGE_TOK * WKV_N * 4 + 3 * WKV_N * 4 + 64;
+    return b;
 }
 
 template <int VER>
-__global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant__ WkvParams p, const int max_tokens) {
+__global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_constant__ WkvParams p, const int max_tokens) {
+    constexpr int KC = WKV_SA_KC, LANES = WKV_N / KC, NT = WKV_SA_THREADS;
     __shared__ WkvShared sm;
     extern __shared__ __align__(16) uint8_t wkv_dyn[];
     trace_stamp(p.trace, 0);
@@ -220,56 +251,124 @@ __global__ void __launch_bounds__(WKV_THREADS) wkv_kernel(const __grid_constant_
     const int si = blockIdx.y;
     const int h = blockIdx.x;
     const int tid = threadIdx.x;
-    const int ig = tid >> 4, j4 = tid & 15;
+    const int ig = tid / LANES, j4 = tid % LANES;
+    const int ch = h * WKV_N;
     const bool fold = (VER == 6) && p.wd2t != nullptr;
-    // the decay-LoRA slice is a weight: fetch it before waiting on the producer kernel
-    __half* wt = reinterpret_cast<__half*>(wkv_dyn);
+    const int Dd = fold ? p.Dd : 0;
+    uint8_t* dyn = wkv_dyn;
+    __half* wt = reinterpret_cast<__half*>(dyn);
+    float* wl = nullptr;
+    __half* ds = nullptr;
+    float* part = nullptr;
     if (fold) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.wd2t + (size_t)h * WKV_N * p.Dd);
-        uint4* dst = reinterpret_cast<uint4*>(wt);
-        for (int i = tid; i < WKV_N * p.Dd / 8; i += WKV_THREADS) dst[i] = src[i];
+        wl = reinterpret_cast<float*>(dyn + (size_t)WKV_N * Dd * 2);
+        ds = reinterpret_cast<__half*>(wl + (size_t)max_tokens * WKV_N);
+        part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ds) + ((((size_t)WKV_STAGE_TOK * Dd * 2) + 15) & ~(size_t)15));
+        dyn = reinterpret_cast<uint8_t*>(part + 2 * WKV_N);
     }
+    const int na = wkv_stage_arrays(VER, fold);
+    float* pre_s = reinterpret_cast<float*>(dyn);
+    float* statics = pre_s + na * WKV_STAGE_TOK * WKV_N;
+    // ---- before the wait: weights and step metadata ----
+    if (fold) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.wd2t + (size_t)h * WKV_N * Dd);
+        uint4* dst = reinterpret_cast<uint4*>(wt);
+        for (int i = tid; i < WKV_N * Dd / 8; i += NT) dst[i] = src[i];
+    }
+    for (int i = tid; i < 3 * WKV_N; i += NT) {
+        const int a = i >> 6, c = i & (WKV_N - 1);
+        float v = 0.f;
+        if (a == 0) v = p.lnx_w[ch + c];
+        else if (a == 1) v = p.lnx_b[ch + c];
+        else if (VER != 7) v = p.u[ch + c];
+        statics[i] = v;
+    }
+    const float bias = fold ? p.decay_bias[ch + (tid & (WKV_N - 1))] : 0.f;
+    const int nslots = p.meta.nslots();
+    const bool live = si < nslots;
+    const int slot = live ? p.meta.slot_id()[si] : 0;
+    const int t0 = live ? p.meta.slot_start()[si] : 0;
+    const int nt = live ? p.meta.slot_count()[si] : 0;
     pdl_wait();
     trace_stamp(p.trace, 1);
-    if (si >= p.meta.nslots()) return;
-    const int slot = p.meta.slot_id()[si];
-    const int t0 = p.meta.slot_start()[si];
-    const int nt = p.meta.slot_count()[si];
+    if (!live) return;
 
+    // ---- one batch of loads: state patch, staged rows, decay-LoRA inputs ----
     float* M = p.state + ((size_t)slot * p.H + h) * (WKV_N * WKV_N);
-    float4 m[4];
+    float m[4][KC];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) m[e] = __ldcs(reinterpret_cast<const float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4));
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int q = 0; q < KC / 4; ++q) {
+            const float4 v4 = __ldcs(reinterpret_cast<const float4*>(M + (ig * 4 + e) * WKV_N + j4 * KC + q * 4));
+            m[e][q * 4] = v4.x; m[e][q * 4 + 1] = v4.y; m[e][q * 4 + 2] = v4.z; m[e][q * 4 + 3] = v4.w;
+        }
+    const bool staged = nt <= WKV_STAGE_TOK;
+    if (staged) {
+        constexpr int UMAX = WKV_STAGE_ARRAYS * WKV_STAGE_TOK * WKV_N / NT;      // 14
+        const int per = nt * WKV_N, total = na * per;
+        const int ndd = fold ? nt * Dd : 0;
+        // two half batches keep the register peak below the one-wave budget
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float val[UMAX / 2];
+#pragma unroll
+            for (int u = 0; u < UMAX / 2; ++u) {
+                const int i = tid + (half * (UMAX / 2) + u) * NT;
+                val[u] = 0.f;
+                if (i < total) {
+                    const int a = i / per, rem = i - a * per;
+                    const size_t at = (size_t)(t0 + (rem >> 6)) * p.ld + ch + (rem & (WKV_N - 1));
+                    const float* src = a == 0 ? p.r : a == 1 ? p.k : a == 2 ? p.v : a == 3 ? p.g : a == 4 ? p.w : a == 5 ? p.a : p.nu;
+                    if (src) val[u] = src[at];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UMAX / 2; ++u) {
+                const int i = tid + (half * (UMAX / 2) + u) * NT;
+                if (i < total) {
+                    const int a = i / per, rem = i - a * per;
+                    pre_s[a * (WKV_STAGE_TOK * WKV_N) + rem] = val[u];
+                }
+            }
+        }
+        for (int i = tid; i < ndd; i += NT) {
+            const int tt = i / Dd;
+            ds[i] = p.d1[a16_index(t0 + tt, i - tt * Dd, p.d1_kq)];
+        }
+    }
 
     const float* w_local = nullptr;
     if (fold) {
         // w[t][c] = exp(-exp(time_decay[c] + sum_k Wd2[c][k] * tanh(Wd1 xw)[t][k]))   
-        const int Dd = p.Dd;
-        float* wl = reinterpret_cast<float*>(wkv_dyn + (size_t)WKV_N * Dd * 2);
-        __half* ds = reinterpret_cast<__half*>(wl + (size_t)max_tokens * WKV_N);
-        float* part = reinterpret_cast<float*>(wkv_dyn + (size_t)WKV_N * Dd * 2 + (size_t)max_tokens * WKV_N * 4 + (((size_t)Dd * 2 + 15) & ~(size_t)15));
         const int c = tid & (WKV_N - 1), qk = tid >> 6;
-        const int kq0 = qk * (Dd >> 2), kq1 = kq0 + (Dd >> 2);
-        const float bias = p.decay_bias[h * WKV_N + c];
+        const int kq0 = qk * (Dd >> 1), kq1 = kq0 + (Dd >> 1);
         for (int tt = 0; tt < nt; ++tt) {
             __syncthreads();
-            for (int k = tid; k < Dd; k += WKV_THREADS) ds[k] = p.d1[a16_index(t0 + tt, k, p.d1_kq)];
-            __syncthreads();
-            float acc = 0.f;
-            for (int k = kq0; k < kq1; ++k) acc = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(ds[k]), acc);
-            part[qk * WKV_N + c] = acc;
-            __syncthreads();
-            if (tid < WKV_N) {
-                const float s = (part[c] + part[WKV_N + c]) + (part[2 * WKV_N + c] + part[3 * WKV_N + c]);
-                wl[tt * WKV_N + c] = expf(-expf(bias + s));
+            const __half* dt = staged ? ds + tt * Dd : ds;
+            if (!staged) {
+                for (int k = tid; k < Dd; k += NT) ds[k] = p.d1[a16_index(t0 + tt, k, p.d1_kq)];
+                __syncthreads();
             }
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int k = kq0; k < kq1; k += 2) {
+                acc0 = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(dt[k]), acc0);
+                acc1 = fmaf(__half2float(wt[(k + 1) * WKV_N + c]), __half2float(dt[k + 1]), acc1);
+            }
+            part[qk * WKV_N + c] = acc0 + acc1;
+            __syncthreads();
+            if (tid < WKV_N) wl[tt * WKV_N + c] = expf(-expf(bias + (part[c] + part[WKV_N + c])));
         }
-        __syncthreads();
         w_local = wl;
     }
-    wkv_slot<VER, false>(p, h, t0, nt, m, sm, w_local, 0);
+    __syncthreads();
+    wkv_slot<VER, false, KC>(p, h, t0, nt, m, sm, w_local, 0, staged ? pre_s : nullptr, WKV_STAGE_TOK * WKV_N, statics);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) __stcs(reinterpret_cast<float4*>(M + (ig * 4 + e) * WKV_N + j4 * 4), m[e]);
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int q = 0; q < KC / 4; ++q)
+            __stcs(reinterpret_cast<float4*>(M + (ig * 4 + e) * WKV_N + j4 * KC + q * 4),
+                   make_float4(m[e][q * 4], m[e][q * 4 + 1], m[e][q * 4 + 2], m[e][q * 4 + 3]));
     trace_stamp(p.trace, 7);
 }
 

@@ -46,6 +46,12 @@ G = 148
 for layer in (8, 9, 10, 11):
     i0 = 1 + layer * per
     for i in range(i0, i0 + per):
+        if types[i] == 6:
+            c = full[i, 8:8 + 3 * 128].reshape(128, 3)
+            base = c[:, 1].min()
+            ent = (c[:, 0] - base) / 1e3; rel = (c[:, 1] - base) / 1e3; p1 = (c[:, 2] - base) / 1e3
+            print(f"  L{layer} pre6 per-CTA (us from first release): entry min/med/max {ent.min():6.2f} {np.median(ent):6.2f} {ent.max():6.2f} | released {rel.min():5.2f} {np.median(rel):5.2f} {rel.max():5.2f} | phase1 done {p1.min():5.2f} {np.median(p1):5.2f} {p1.max():5.2f} | slowest clusters {sorted(set((np.argsort(p1)[-8:] // 8).tolist()))}")
+            continue
         if types[i] < 1000000: continue
         c = full[i, 8:8 + 3 * G].reshape(G, 3)
         ok = c[:, 2] > 0
