@@ -968,7 +968,7 @@ void b200rwkv_engine::build(const StFile& st) {
             std::vector<SegDesc> sv;
             sv.push_back(a16_seg(Fk, f0, Fl, 0, C, a_x[0], a_kk, ACT_RELU2, nullptr));
             sv.push_back(f32_seg(st.get(f + "receptance.weight"), c0, Cl, 0, C, a_x[1], f_rr, Cl, ACT_SIGMOID, nullptr));
-            ly.ffn.push_back(make_launch(sv));
+            ly.ffn.push_back(make_launch(sv, getenv("B200RWKV_KR_GRID") ? atoi(getenv("B200RWKV_KR_GRID")) : 0));
         }
         {
             std::vector<SegDesc> sv;

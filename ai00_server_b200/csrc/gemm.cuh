@@ -305,8 +305,14 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
                 const int mmax = min(nrows, MT * 16);
                 if (out_mode == OUT_F32) {
                     float* o = reinterpret_cast<float*>(outp) + n;
+                    if (MT == 1) {          // decode shape: straight from registers, all 16 stores in flight
+#pragma unroll
+                        for (int m = 0; m < 16; ++m)
+                            if (m < mmax) o[(size_t)m * ldo] = apply_act(v[0][m] + bias, act);
+                    } else {
 #pragma unroll 1
-                    for (int m = 0; m < mmax; ++m) o[(size_t)m * ldo] = apply_act(lv[m] + bias, act);
+                        for (int m = 0; m < mmax; ++m) o[(size_t)m * ldo] = apply_act(lv[m] + bias, act);
+                    }
                 } else {
                     __half* base = reinterpret_cast<__half*>(outp);
                     int nn = n;

@@ -101,8 +101,31 @@ def make_tokens(n_steps: int, batch: int, vocab: int):
     return rng.integers(1, min(vocab, 65530), size=(batch, n_steps), dtype=np.int64)
 
 
+def host_threads() -> int:
+    """Threads the CPU arm should use: physical cores inside this process' affinity mask and cgroup CPU quota.
+    (Measured on the GPU box: 128 OpenMP threads on its 64 cores run the same step 18x slower than 64.)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            n = min(n, phys)
+    except Exception:
+        n = max(1, n // 2)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_arm(weights, batch: int, steps: int, warmup: int, toks_bt: np.ndarray):
     """Times the C/OpenMP oracle on the host cores: `steps` decode steps of the same workload."""
+    if "OMP_NUM_THREADS" not in os.environ:        # must be set before libgomp is loaded
+        os.environ["OMP_NUM_THREADS"] = str(host_threads())
+    os.environ.setdefault("OMP_PROC_BIND", "false")
     from ai00_server_b200 import build
     from oracle import ref_c
     if not os.path.exists(ref_c.LIB_PATH):
@@ -249,9 +272,16 @@ def main():
         return
     gemm_gbs = wbytes / (prof_ms[0] * 1e-3) / 1e9 if prof_ms[0] > 0 else 0.0
     alg_bytes = synth.algorithmic_bytes_per_step(shape, BATCH) / world
+    traffic = None       # DRAM bytes of the same launches from the committed ncu capture (N = 1 capture of this workload)
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if world == 1 and PRESET == "v6-7b" and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj["layers"] * sum(x["dram_bytes"] for x in tj["per_layer_gemm_launches"]) + tj["head"]["algorithmic_weight_bytes"]
     roofline = {"bound": "hbm", "kernel": "gemm_kernel<1> (tcgen05 projection GEMM: all launches of one step, per GPU)",
                 "achieved": gemm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gemm_gbs / peaks["hbm_gbs"],
-                "peak_source": f"MEASURED_PEAKS.json ({peak_src})", "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json ({peak_src})", "traffic": traffic,
+                "traffic_note": "per step, summed over the same projection launches as `achieved`: ncu dram read+write bytes of one "
+                                "captured layer x 32 + the head's algorithmic bytes (profiles/r01_gemm_traffic.json)",
                 "algorithmic_bytes_per_step_gemm": int(wbytes), "gemm_ms_per_step": float(prof_ms[0]),
                 "gemm_launches_per_step": int(prof_n[0]),
                 "note": "per-launch CUDA events on the engine stream in an un-graphed pass (includes launch gaps); "
