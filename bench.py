@@ -104,6 +104,13 @@ def make_tokens(n_steps: int, batch: int, vocab: int):
 def host_threads() -> int:
     """Threads the CPU arm should use: physical cores inside this process' affinity mask and cgroup CPU quota.
     (Measured on the GPU box: 128 OpenMP threads on its 64 cores run the same step 18x slower than 64.)"""
+    try:                       # torch sizes its intra-op pool to the physical cores it may use; the default arm's CPU leg
+        import torch           # runs with exactly this count (64 on the GPU box), so both arms agree
+        n = int(torch.get_num_threads())
+        if n >= 1:
+            return n
+    except Exception:
+        pass
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
         import psutil
