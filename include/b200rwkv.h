@@ -150,7 +150,12 @@ int32_t b200rwkv_last_hidden(b200rwkv_engine*, float* out, size_t cap);
  * row-major; returns the column count (negative status on error).  Not on the product path. */
 int32_t b200rwkv_debug_read(b200rwkv_engine*, const char* name, float* out, size_t cap);
 
-/* Profiling aid: per-phase timer stamps of the last whole-step kernel (B200RWKV_TRACE=1). */
+/* Profiling aid.  With B200RWKV_TRACE=1 and the whole-step kernel: per-phase timer stamps of the last step
+ * (out = [4 CTAs][nphase][12]).  With B200RWKV_STEP_TRACE=1 and the per-op chain: one row of 512 uint64 per launch of
+ * the last captured step shape (out = [nphase = launches][512]): globaltimer stamps of CTA 0 in [0..7] (entry, past
+ * griddepcontrol.wait, phase marks, exit), then {SM id, last MMA issued, exit} of every projection CTA (or {entry,
+ * released, phase 1 done} of every CTA of the fused RWKV-6 front-half kernel); types[i] = 0 LN, 2 WKV, 6 front half,
+ * 1000000 + weight MiB for a projection launch. */
 int32_t b200rwkv_debug_trace(b200rwkv_engine*, uint64_t* out, size_t cap, int32_t* types, int32_t* nphase);
 
 /* Profiling aid: one projection launch class timed in isolation over all layers. */
