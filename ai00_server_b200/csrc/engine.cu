@@ -398,6 +398,8 @@ struct b200rwkv_engine {
                   X... extra);
     bool fold_wd2 = false, lora_cc = false;
     int gemm_ring = 2;            // GemmCfg RING mode of the decode-shaped projection kernel
+    bool gemm_fin = false;        // experimental designated-finisher stream-K (gemm.cuh), B200RWKV_FINISHER=1
+    int sk_grid = 0;              // experimental: cap of the stream-K grid (B200RWKV_SK_GRID, e.g. 128 = 16 CTAs per GPC)
     int prefetch_blocks = 16;     // L2 prefetch depth (32 KB blocks per CTA) into the next projection launch
     bool fused_pre = true, ln_cluster = true;     // decode-shaped cluster kernels of pre6.cuh
     bool fused_pre_ok = false, ln_cluster_ok = false;
@@ -535,6 +537,7 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
             for (int cand = num_sms; cand * 4 >= num_sms * 3; --cand)
                 if (tile % cand == 0) { g.grid = cand; break; }
     } else if (tile <= num_sms && tile * 10 >= num_sms * 9) g.grid = tile;
+    if (sk_grid > 0 && force_grid <= 0 && g.grid != tile && (tile <= num_sms || tile % g.grid != 0)) g.grid = std::min(g.grid, sk_grid);
     const int per_cta = std::max(1, blk / g.grid);
     g.p.max_contrib = cdiv(kbmax, per_cta) + 1;
     g.p.counters = (unsigned*)dalloc((size_t)tile * 4, true);
@@ -590,6 +593,7 @@ void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, P
     switch (MT) {
         case 1:
             if (gemm_ring == 1) launch_k(gemm_kernel<1, 1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            else if (gemm_fin) launch_k(gemm_kernel<1, 2, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             else if (gemm_ring == 2) launch_k(gemm_kernel<1, 2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             else launch_k(gemm_kernel<1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             break;
@@ -629,9 +633,12 @@ void b200rwkv_engine::build(const StFile& st) {
     CK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 1>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 2>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 2>::SMEM_BYTES));
     if (const char* v = getenv("B200RWKV_GEMM_HALF")) gemm_ring = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("B200RWKV_GEMM_RING")) gemm_ring = atoi(v);
     if (const char* v = getenv("B200RWKV_PREFETCH_BLOCKS")) prefetch_blocks = std::max(0, atoi(v));
+    if (const char* v = getenv("B200RWKV_FINISHER")) gemm_fin = atoi(v) != 0;
+    if (const char* v = getenv("B200RWKV_SK_GRID")) sk_grid = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_LORA_CC")) lora_cc = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_FUSED_PRE")) fused_pre = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_LN_CLUSTER")) ln_cluster = atoi(v) != 0;

@@ -349,3 +349,31 @@ def test_short_ragged_steps_use_the_cluster_kernels(models, preset):
     for s in range(3):
         got = m.state.back(s)
         assert rel_err(got, sts[s]) <= 5 * REL_TOL
+
+
+@pytest.mark.skipif(os.environ.get("B200RWKV_TEST_EXPERIMENTAL") != "1",
+                    reason="kernel paths written at the end of round 1 that have not run on hardware yet; opt-in")
+@pytest.mark.parametrize("preset", ["small6", "tiny7"])
+def test_experimental_designated_finisher_stream_k(models, preset):
+    """Designated-finisher stream-K (gemm.cuh, B200RWKV_FINISHER=1) must reproduce the last-arriver path bit for bit on the
+    same grid (same fixed summation order), and match the oracle."""
+    base_env = {"B200RWKV_SK_GRID": "128", "B200RWKV_OLD_GRID": "1"}
+    a, orc, _ = models(preset, mega=False, env=dict(base_env, B200RWKV_FINISHER="1"))
+    b, _, _ = models(preset, mega=False, env=base_env)
+    rng = np.random.default_rng(5)
+    toks = rng.integers(1, 500, size=(5, 3))
+    outs = []
+    for m in (a, b):
+        for s in range(3):
+            m.state.load(m.state.init(), s)
+        rows = None
+        for i in range(5):
+            rows = m.infer_raw([0, 1, 2], [1, 1, 1], toks[i].tolist(), [capi.OPTION_LAST] * 3)
+        outs.append(np.concatenate(rows))
+    assert np.array_equal(outs[0], outs[1])
+    sts = [orc.state_init() for _ in range(3)]
+    for s in range(3):
+        want = None
+        for i in range(5):
+            want, sts[s] = orc.run([int(toks[i, s])], sts[s])
+        assert rel_err(outs[0][s:s + 1], want) <= REL_TOL
