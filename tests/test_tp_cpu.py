@@ -56,7 +56,8 @@ def test_handle_all_gather_over_gloo_world2(tmp_path):
             assert allh[r, 0] == 200 + r and (allh[r, 1:] == r + 1).all()
         dist.barrier()
         dist.destroy_process_group()
-        print("rank", rank, "ok")
+        sys.stdout.write("rank %d ok" % rank + chr(10))      # one write per rank: the two ranks share the pipe
+        sys.stdout.flush()
     """))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(script)]
