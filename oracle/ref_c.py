@@ -15,7 +15,9 @@ _P = C.c_void_p
 
 _LAYER_FIELDS = ["ln1_w", "ln1_b", "ln2_w", "ln2_b", "mix_x", "mix_w", "mix_k", "mix_v", "mix_r", "mix_g", "mix_w1", "mix_w2",
                  "decay", "decay_w1", "decay_w2", "first", "wr", "wk", "wv", "wg", "wo", "lnx_w", "lnx_b", "fmix_k", "fmix_r",
-                 "fk", "fr", "fv"]
+                 "fk", "fr", "fv",
+                 "x_r", "x_w", "x_k", "x_v", "x_a", "x_g", "w0", "w1", "w2", "a0", "a1", "a2", "v0", "v1", "v2", "g1", "g2",
+                 "k_k", "k_a", "r_k", "fx_k"]
 
 
 class RefLayer(C.Structure):
@@ -23,7 +25,7 @@ class RefLayer(C.Structure):
 
 
 class RefModel(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("version", "L", "C", "F", "V", "H", "N", "Dm", "Dd", "act_f16")] + \
+    _fields_ = [(n, C.c_int32) for n in ("version", "L", "C", "F", "V", "H", "N", "Dm", "Dd", "act_f16", "Dw", "Da", "Dv", "Dg")] + \
                [(n, _P) for n in ("emb", "ln0_w", "ln0_b", "lnout_w", "lnout_b", "head", "layers")]
 
 
@@ -36,14 +38,14 @@ def _lib():
 
 
 class RefC:
-    """v5/v6 decode step on B slots; state is [B, L, N+2, C] f32 (web-rwkv layout per slot)."""
+    """v5/v6/v7 decode step on B slots; state is [B, L, N+2, C] f32 (web-rwkv layout per slot)."""
 
     def __init__(self, weights: dict[str, np.ndarray], act: str = "f16"):
         self.lib = _lib()
         self.w = weights
         i = O.model_info(weights)
-        if i.version not in (5, 6):
-            raise ValueError("the C oracle covers v5/v6 (the benchmarked path); v7 is checked by the NumPy oracle")
+        if i.version not in (5, 6, 7):
+            raise ValueError("unsupported model version")
         self.info = i
 
         def p(name):
@@ -52,11 +54,24 @@ class RefC:
             return a.ctypes.data
 
         self._layers = (RefLayer * i.num_layer)()
-        v6 = i.version == 6
+        v6, v7 = i.version == 6, i.version == 7
+        dims = {"Dw": 0, "Da": 0, "Dv": 0, "Dg": 0}
         for l in range(i.num_layer):
             b, a, f = f"blocks.{l}.", f"blocks.{l}.att.", f"blocks.{l}.ffn."
             ly = self._layers[l]
             ly.ln1_w, ly.ln1_b, ly.ln2_w, ly.ln2_b = p(b + "ln1.weight"), p(b + "ln1.bias"), p(b + "ln2.weight"), p(b + "ln2.bias")
+            ly.wr, ly.wk, ly.wv, ly.wo = (p(a + n + ".weight") for n in ("receptance", "key", "value", "output"))
+            ly.lnx_w, ly.lnx_b = p(a + "ln_x.weight"), p(a + "ln_x.bias")
+            ly.fk, ly.fv = p(f + "key.weight"), p(f + "value.weight")
+            if v7:
+                for n in ("x_r", "x_w", "x_k", "x_v", "x_a", "x_g", "w0", "w1", "w2", "a0", "a1", "a2", "g1", "g2", "k_k", "k_a", "r_k"):
+                    setattr(ly, n, p(a + n))
+                if l > 0:
+                    ly.v0, ly.v1, ly.v2 = p(a + "v0"), p(a + "v1"), p(a + "v2")
+                    dims["Dv"] = weights[a + "v1"].shape[0]
+                ly.fx_k = p(f + "x_k")
+                dims["Dw"], dims["Da"], dims["Dg"] = (weights[a + n].shape[0] for n in ("w1", "a1", "g1"))
+                continue
             for n in ("k", "v", "r", "g"):
                 setattr(ly, "mix_" + n, p(a + "time_mix_" + n))
             if v6:
@@ -64,13 +79,13 @@ class RefC:
                 ly.mix_w1, ly.mix_w2 = p(a + "time_mix_w1"), p(a + "time_mix_w2")
                 ly.decay_w1, ly.decay_w2 = p(a + "time_decay_w1"), p(a + "time_decay_w2")
             ly.decay, ly.first = p(a + "time_decay"), p(a + "time_first")
-            ly.wr, ly.wk, ly.wv, ly.wg, ly.wo = (p(a + n + ".weight") for n in ("receptance", "key", "value", "gate", "output"))
-            ly.lnx_w, ly.lnx_b = p(a + "ln_x.weight"), p(a + "ln_x.bias")
+            ly.wg = p(a + "gate.weight")
             ly.fmix_k, ly.fmix_r = p(f + "time_mix_k"), p(f + "time_mix_r")
-            ly.fk, ly.fr, ly.fv = p(f + "key.weight"), p(f + "receptance.weight"), p(f + "value.weight")
+            ly.fr = p(f + "receptance.weight")
         m = RefModel()
         m.version, m.L, m.C, m.F, m.V, m.H, m.N = i.version, i.num_layer, i.num_emb, i.num_hidden, i.num_vocab, i.num_head, i.head_size
         m.Dm, m.Dd, m.act_f16 = i.time_mix_adapter, i.time_decay_adapter, int(act == "f16")
+        m.Dw, m.Da, m.Dv, m.Dg = dims["Dw"], dims["Da"], dims["Dv"], dims["Dg"]
         m.emb, m.head = p("emb.weight"), p("head.weight")
         m.ln0_w, m.ln0_b = p("blocks.0.ln0.weight"), p("blocks.0.ln0.bias")
         m.lnout_w, m.lnout_b = p("ln_out.weight"), p("ln_out.bias")

@@ -1,4 +1,4 @@
-/* CPU oracle, C/OpenMP restatement of the RWKV v5/v6 decode step (one token per slot).
+/* CPU oracle, C/OpenMP restatement of the RWKV v5/v6/v7 decode step (one token per slot).
  *
  * TEST INFRASTRUCTURE ONLY: used by tests/ (cross-checked against oracle/rwkv_numpy.py and the
  * committed goldens) and as bench.py's `cpu_baseline` / `--impl reference` arm, where it stands
@@ -6,7 +6,8 @@
  * (no Rust toolchain, no Vulkan loader).  PARITY UNPINNED: the reference
  * holds no golden vectors for this path; see oracle/rwkv_numpy.py for what anchors the math.
  *
- * Math: SURVEY.md App. A (BlinkDL rwkv pip model.py att_one_v6_0 / ffn_one_v6, att_one_v5_2),
+ * Math: SURVEY.md App. A (BlinkDL rwkv pip model.py att_one_v6_0 / ffn_one_v6, att_one_v5_2) and App. B (RWKV-LM
+ * rwkv_v7_demo_rnn.py: delta-rule state update, kk normalisation, value residual, bonus term),
  * weights in the `.st` layout of /root/reference/assets/scripts/convert_safetensors.py:22-101
  * (all f16, matrices [out, in]).  State per slot: (L, N+2, C) f32 == web-rwkv [C, N+2, L, 1]
  * (reference crates/ai00-core/src/run.rs:987).
@@ -36,10 +37,19 @@ typedef struct {
     /* ffn */
     const h16 *fmix_k, *fmix_r;
     const h16 *fk, *fr, *fv;                                      /* [F, C], [C, C], [C, F] */
+    /* v7 (x070) */
+    const h16 *x_r, *x_w, *x_k, *x_v, *x_a, *x_g;                 /* static token-shift mixes [C] */
+    const h16 *w0, *w1, *w2;                                      /* decay LoRA: [C], [Dw, C], [C, Dw] */
+    const h16 *a0, *a1, *a2;                                      /* in-context learning rate: [C], [Da, C], [C, Da] */
+    const h16 *v0, *v1, *v2;                                      /* value residual gate (layers > 0): [C], [Dv, C], [C, Dv] */
+    const h16 *g1, *g2;                                           /* output gate: [Dg, C], [C, Dg] */
+    const h16 *k_k, *k_a, *r_k;                                   /* [C] */
+    const h16 *fx_k;                                              /* channel-mix token-shift mix [C] */
 } RefLayer;
 
 typedef struct {
     int32_t version, L, C, F, V, H, N, Dm, Dd, act_f16;
+    int32_t Dw, Da, Dv, Dg;                                       /* v7 LoRA ranks */
     const h16 *emb, *ln0_w, *ln0_b, *lnout_w, *lnout_b, *head;
     const RefLayer* layers;
 } RefModel;
@@ -90,8 +100,160 @@ static void round_rows(const float* src, float* dst, size_t n, int on) {
 
 static inline float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+/* y[b][n] += bias[n] (optional), then f applied elementwise */
+static void add_bias(float* y, const h16* bias, int B, int N) {
+    for (int b = 0; b < B; ++b)
+        for (int n = 0; n < N; ++n) y[(size_t)b * N + n] += (float)bias[n];
+}
+
+/* two-stage LoRA: out[B, C] = W2 [C, D] @ q(act1(W1 [D, C] @ q(x)));  act1: 0 none, 1 tanh, 2 sigmoid */
+static void lora2(const h16* W1, const h16* W2, int D, int C, const float* x, int B, int act1, int q, float* in, float* mid, float* out) {
+    round_rows(x, in, (size_t)B * C, q);
+    gemm(W1, D, C, in, B, mid);
+    for (size_t i = 0; i < (size_t)B * D; ++i) {
+        float t = mid[i];
+        if (act1 == 1) t = tanhf(t);
+        else if (act1 == 2) t = sigmoidf_(t);
+        mid[i] = q16(t, q);
+    }
+    gemm(W2, C, D, mid, B, out);
+}
+
+/* RWKV-7 decode step (oracle/rwkv_numpy.py::_att_v7 / _ffn_v7 is the NumPy twin).
+ * State rows 1..N of a layer hold S[h][i (value)][j (key)] at row 1+i, column h*N+j. */
+static int ref_decode_step_v7(const RefModel* m, int B, const int32_t* tokens, float* state, float* logits) {
+    const int C = m->C, F = m->F, V = m->V, H = m->H, N = m->N, L = m->L, q = m->act_f16;
+    const size_t BC = (size_t)B * C;
+    const size_t per_slot = (size_t)L * (N + 2) * C;
+    const int FM = F > C ? F : C;
+    int Dmax = m->Dw;
+    if (m->Da > Dmax) Dmax = m->Da;
+    if (m->Dv > Dmax) Dmax = m->Dv;
+    if (m->Dg > Dmax) Dmax = m->Dg;
+    float *x = (float*)malloc(4 * BC), *xx = (float*)malloc(4 * BC), *sx = (float*)malloc(4 * BC);
+    float *tmp = (float*)malloc(4 * (size_t)B * FM), *in = (float*)malloc(4 * (size_t)B * FM), *mid = (float*)malloc(4 * (size_t)B * Dmax);
+    float* xs[6];
+    for (int i = 0; i < 6; ++i) xs[i] = (float*)malloc(4 * BC);
+    float *r = (float*)malloc(4 * BC), *k = (float*)malloc(4 * BC), *v = (float*)malloc(4 * BC), *g = (float*)malloc(4 * BC);
+    float *dec = (float*)malloc(4 * BC), *a = (float*)malloc(4 * BC), *kkn = (float*)malloc(4 * BC), *vfirst = (float*)malloc(4 * BC);
+    float *out = (float*)malloc(4 * BC), *kk = (float*)malloc(4 * (size_t)B * F);
+
+    for (int b = 0; b < B; ++b) {
+        int t = tokens[b];
+        if (t < 0) t = 0;
+        if (t >= V) t = V - 1;
+        for (int i = 0; i < C; ++i) tmp[i] = (float)m->emb[(size_t)t * C + i];
+        layer_norm(tmp, m->ln0_w, m->ln0_b, C, x + (size_t)b * C);
+    }
+    for (int l = 0; l < L; ++l) {
+        const RefLayer* ly = &m->layers[l];
+        /* ---------------- time mix ---------------- */
+        for (int b = 0; b < B; ++b) {
+            const float* st = state + b * per_slot + (size_t)l * (N + 2) * C;
+            layer_norm(x + (size_t)b * C, ly->ln1_w, ly->ln1_b, C, xx + (size_t)b * C);
+            for (int i = 0; i < C; ++i) sx[(size_t)b * C + i] = st[i] - xx[(size_t)b * C + i];
+        }
+        const h16* mus[6] = {ly->x_r, ly->x_w, ly->x_k, ly->x_v, ly->x_a, ly->x_g};
+        for (int j = 0; j < 6; ++j)
+            for (size_t i = 0; i < BC; ++i) xs[j][i] = xx[i] + sx[i] * (float)mus[j][i % C];
+        round_rows(xs[0], in, BC, q); gemm(ly->wr, C, C, in, B, r);
+        round_rows(xs[2], in, BC, q); gemm(ly->wk, C, C, in, B, k);
+        round_rows(xs[3], in, BC, q); gemm(ly->wv, C, C, in, B, v);
+        /* decay = exp(-exp(-0.5) * sigmoid(w0 + W2 tanh(W1 xw))) */
+        lora2(ly->w1, ly->w2, m->Dw, C, xs[1], B, 1, q, in, mid, dec);
+        add_bias(dec, ly->w0, B, C);
+        for (size_t i = 0; i < BC; ++i) dec[i] = expf(-0.606531f * sigmoidf_(dec[i]));
+        /* a = sigmoid(a0 + A2 (A1 xa)) */
+        lora2(ly->a1, ly->a2, m->Da, C, xs[4], B, 0, q, in, mid, a);
+        add_bias(a, ly->a0, B, C);
+        for (size_t i = 0; i < BC; ++i) a[i] = sigmoidf_(a[i]);
+        /* g = G2 sigmoid(G1 xg) */
+        lora2(ly->g1, ly->g2, m->Dg, C, xs[5], B, 2, q, in, mid, g);
+        /* kk = normalize_head(k * k_k);  k = k * (1 + (a - 1) * k_a) */
+        for (int b = 0; b < B; ++b)
+            for (int h = 0; h < H; ++h) {
+                const size_t o = (size_t)b * C + (size_t)h * N;
+                float ss = 0.f;
+                for (int j = 0; j < N; ++j) { const float t = k[o + j] * (float)ly->k_k[h * N + j]; kkn[o + j] = t; ss += t * t; }
+                float nrm = sqrtf(ss);
+                if (nrm < 1e-12f) nrm = 1e-12f;
+                for (int j = 0; j < N; ++j) kkn[o + j] /= nrm;
+            }
+        for (size_t i = 0; i < BC; ++i) k[i] = k[i] * (1.0f + (a[i] - 1.0f) * (float)ly->k_a[i % C]);
+        if (l == 0) {
+            memcpy(vfirst, v, 4 * BC);
+        } else {
+            lora2(ly->v1, ly->v2, m->Dv, C, xs[3], B, 0, q, in, mid, tmp);
+            add_bias(tmp, ly->v0, B, C);
+            for (size_t i = 0; i < BC; ++i) v[i] = v[i] + (vfirst[i] - v[i]) * sigmoidf_(tmp[i]);
+        }
+#pragma omp parallel for collapse(2) schedule(static)
+        for (int b = 0; b < B; ++b)
+            for (int h = 0; h < H; ++h) {
+                float* st = state + b * per_slot + (size_t)l * (N + 2) * C;
+                const size_t o = (size_t)b * C + (size_t)h * N;
+                const float *rb = r + o, *kb = k + o, *vb = v + o, *wb = dec + o, *ab = a + o, *nb = kkn + o;
+                float oh[64];
+                for (int i = 0; i < N; ++i) {
+                    float* S = st + (size_t)(1 + i) * C + h * N;      /* S[i (value)][j (key)] */
+                    float sa = 0.f;
+                    for (int j = 0; j < N; ++j) sa += S[j] * (-nb[j]);
+                    float acc = 0.f;
+                    for (int j = 0; j < N; ++j) {
+                        S[j] = S[j] * wb[j] + sa * (nb[j] * ab[j]) + vb[i] * kb[j];
+                        acc += S[j] * rb[j];
+                    }
+                    oh[i] = acc;
+                }
+                float mean = 0.f;
+                for (int j = 0; j < N; ++j) mean += oh[j];
+                mean /= (float)N;
+                float var = 0.f;
+                for (int j = 0; j < N; ++j) { float d = oh[j] - mean; var += d * d; }
+                var /= (float)N;
+                const float rstd = 1.0f / sqrtf(var + 64e-5f);
+                float bonus = 0.f;
+                for (int j = 0; j < N; ++j) bonus += rb[j] * kb[j] * (float)ly->r_k[h * N + j];
+                for (int j = 0; j < N; ++j) {
+                    const int c = h * N + j;
+                    const float y = (oh[j] - mean) * rstd * (float)ly->lnx_w[c] + (float)ly->lnx_b[c] + bonus * vb[j];
+                    out[(size_t)b * C + c] = y * g[(size_t)b * C + c];
+                }
+            }
+        for (int b = 0; b < B; ++b) {
+            float* st = state + b * per_slot + (size_t)l * (N + 2) * C;
+            memcpy(st, xx + (size_t)b * C, 4 * (size_t)C);
+        }
+        round_rows(out, in, BC, q);
+        gemm(ly->wo, C, C, in, B, tmp);
+        for (size_t i = 0; i < BC; ++i) x[i] += tmp[i];
+        /* ---------------- channel mix ---------------- */
+        for (int b = 0; b < B; ++b) {
+            float* st = state + b * per_slot + (size_t)l * (N + 2) * C + (size_t)(N + 1) * C;
+            layer_norm(x + (size_t)b * C, ly->ln2_w, ly->ln2_b, C, xx + (size_t)b * C);
+            for (int i = 0; i < C; ++i) {
+                const float cur = xx[(size_t)b * C + i];
+                xs[0][(size_t)b * C + i] = cur + (st[i] - cur) * (float)ly->fx_k[i];
+                st[i] = cur;
+            }
+        }
+        round_rows(xs[0], in, BC, q); gemm(ly->fk, F, C, in, B, kk);
+        for (size_t i = 0; i < (size_t)B * F; ++i) { float t = kk[i] > 0.f ? kk[i] : 0.f; kk[i] = q16(t * t, q); }
+        gemm(ly->fv, C, F, kk, B, tmp);
+        for (size_t i = 0; i < BC; ++i) x[i] += tmp[i];
+    }
+    for (int b = 0; b < B; ++b) layer_norm(x + (size_t)b * C, m->lnout_w, m->lnout_b, C, xx + (size_t)b * C);
+    round_rows(xx, in, BC, q);
+    gemm(m->head, V, C, in, B, logits);
+    free(x); free(xx); free(sx); free(tmp); free(in); free(mid);
+    for (int i = 0; i < 6; ++i) free(xs[i]);
+    free(r); free(k); free(v); free(g); free(dec); free(a); free(kkn); free(vfirst); free(out); free(kk);
+    return 0;
+}
+
 /* One decode step for B slots.  tokens[B]; state [B][L][N+2][C] updated in place; logits [B][V]. */
 int ref_decode_step(const RefModel* m, int B, const int32_t* tokens, float* state, float* logits) {
+    if (m->version == 7) return ref_decode_step_v7(m, B, tokens, state, logits);
     const int C = m->C, F = m->F, V = m->V, H = m->H, N = m->N, L = m->L, q = m->act_f16;
     const size_t BC = (size_t)B * C;
     const size_t per_slot = (size_t)L * (N + 2) * C;

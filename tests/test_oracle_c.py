@@ -15,7 +15,8 @@ if not os.path.exists(ref_c.LIB_PATH):
     build.build_oracle()
 
 
-@pytest.mark.parametrize("preset,act", [("tiny6", "f16"), ("tiny6", "f32"), ("tiny5", "f16"), ("small6", "f16")])
+@pytest.mark.parametrize("preset,act", [("tiny6", "f16"), ("tiny6", "f32"), ("tiny5", "f16"), ("small6", "f16"), ("tiny7", "f16"),
+                                        ("tiny7", "f32")])
 def test_c_oracle_matches_numpy_oracle(preset, act):
     w = O.parse_st(synth.make_st(preset, 0))
     rc, orc = ref_c.RefC(w, act), O.Oracle(w, act)
@@ -35,7 +36,7 @@ def test_c_oracle_matches_numpy_oracle(preset, act):
         assert np.abs(st[b] - sts[b]).max() <= 10 * tol * max(1.0, np.abs(sts[b]).max())
 
 
-@pytest.mark.parametrize("preset", ["tiny5", "tiny6"])
+@pytest.mark.parametrize("preset", ["tiny5", "tiny6", "tiny7"])
 def test_c_oracle_matches_goldens(golden_dir, preset):
     g = np.load(os.path.join(golden_dir, f"model_{preset}.npz"))
     w = O.parse_st(synth.make_st(preset, 0))
