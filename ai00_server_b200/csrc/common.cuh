@@ -256,6 +256,42 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 
 // Programmatic dependent launch: everything before this call may overlap the tail of the
 // preceding kernel in the stream/graph (weights are immutable, so weight prefetch may).
+// ---------------------------------------------------------------------------------------
+// Tensor-parallel rendezvous folded into the consumer kernel (opt-in, B200RWKV_TP_FOLD=1; written at the end of round 1,
+// NOT yet run on hardware).  The default path launches a one-warp `tp_barrier_kernel` between a row-parallel projection and
+// the LN stage that sums all ranks' partials: ~5 us per rendezvous (launch, flag round trip over NVLink, dependent release),
+// 65 per step.  Folded: every CTA of the consumer calls tp_rendezvous() right after griddepcontrol.wait (its own rank's
+// producer is complete and flushed): CTA 0 tells every peer "rank r reached site k of step seq", every CTA waits until all
+// peers said the same.  The epoch is seq * nb + k + 1 with seq uploaded with the step metadata, so nothing on the device
+// has to count and a captured graph replays correctly; flags are monotonic, compared with >=.
+// ---------------------------------------------------------------------------------------
+struct TpFold {
+    unsigned* flags[8];     // flags[q]: rank q's flag array [8] (peer-mapped for q != rank); a region of its own
+    const int* seq;         // step sequence number (meta[4])
+    int rank, world;        // world <= 1: no-op
+    int k, nb;              // rendezvous site of this launch, sites per step
+};
+__device__ __forceinline__ void tp_rendezvous(const TpFold& f) {
+    if (f.world <= 1) return;
+    const unsigned e = (unsigned)(*f.seq) * (unsigned)f.nb + (unsigned)f.k + 1u;
+    if ((int)threadIdx.x < f.world) {
+        const int q = threadIdx.x;
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.flags[q] + f.rank), "r"(e) : "memory");
+        }
+        SpinGuard sg_;
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.flags[f.rank] + q) : "memory");
+            if (v >= e) break;
+            sg_.poll(6u, (unsigned)q, e, v);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
 // profiling aid: globaltimer stamp i of this launch's trace row (CTA 0, thread 0 only; `tr` is null in production)
 __device__ __forceinline__ void trace_stamp(unsigned long long* tr, const int i) {
     if (tr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {

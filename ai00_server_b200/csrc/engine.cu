@@ -398,6 +398,9 @@ struct b200rwkv_engine {
                   X... extra);
     bool fold_wd2 = false, lora_cc = false;
     int gemm_ring = 2;            // GemmCfg RING mode of the decode-shaped projection kernel
+    bool tp_fold = false;         // experimental: rendezvous folded into the LN kernels (common.cuh TpFold), B200RWKV_TP_FOLD=1
+    TpFold tpf;                   // template of the per-launch descriptor (flags, seq, rank, world, nb)
+    int step_seq = 0;             // step sequence number uploaded as meta[4]
     bool gemm_fin = false;        // experimental designated-finisher stream-K (gemm.cuh), B200RWKV_FINISHER=1
     int sk_grid = 0;              // experimental: cap of the stream-K grid (B200RWKV_SK_GRID, e.g. 128 = 16 CTAs per GPC)
     int prefetch_blocks = 16;     // L2 prefetch depth (32 KB blocks per CTA) into the next projection launch
@@ -638,6 +641,7 @@ void b200rwkv_engine::build(const StFile& st) {
     if (const char* v = getenv("B200RWKV_GEMM_RING")) gemm_ring = atoi(v);
     if (const char* v = getenv("B200RWKV_PREFETCH_BLOCKS")) prefetch_blocks = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_FINISHER")) gemm_fin = atoi(v) != 0;
+    if (const char* v = getenv("B200RWKV_TP_FOLD")) tp_fold = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_SK_GRID")) sk_grid = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_LORA_CC")) lora_cc = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_FUSED_PRE")) fused_pre = atoi(v) != 0;
@@ -1051,6 +1055,12 @@ void b200rwkv_engine::finalize_tp() {
     }
     lnout.n_parts = parts_of(off_part_ffn, split_ffn, lnout.parts);
     if (ver != 7) { lnout.n_gate = world; lnout.gate_cl = Cl; gates_of(lnout.gates); }
+    memset(&tpf, 0, sizeof(tpf));
+    for (int q = 0; q < world; ++q) tpf.flags[q] = (unsigned*)(peer_base[q] + off_flags + 64);     // own 32 bytes of the flag area
+    tpf.seq = d_meta + 4;
+    tpf.rank = rank;
+    tpf.world = (tp_fold && world > 1) ? world : 0;
+    tpf.nb = 2 * L;
     memset(&tpbar, 0, sizeof(tpbar));
     for (int q = 0; q < world; ++q) tpbar.flags[q] = (unsigned*)(peer_base[q] + off_flags);
     tpbar.epoch = d_epoch;
@@ -1246,15 +1256,20 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
         launch_gemm_chained(g, MT);
     };
     if (!(sk & 1)) launch_k(embed_ln0_kernel, dim3(rows), dim3(LN_THREADS), 0, embed, KC_LN, s, prof);
-    auto launch_ln = [&](const LnMixParams& lp0) {
+    const bool fold = tpf.world > 1;          // rendezvous inside the consumer kernels instead of tp_barrier_kernel launches
+    auto site = [&](int k) { TpFold f = tpf; f.k = k; if (k < 0) f.world = 0; return f; };
+    auto launch_ln = [&](const LnMixParams& lp0, int k) {
         if (sk & 1) return;
         LnMixParams lp = lp0;
         lp.trace = tr_next(0);
+        lp.tp = site(fold ? k : -1);
         if (ln_cluster_ok && MT == 1) {
             launch_cluster = PRE_CLUSTER;
-            launch_k(ln_mix_cluster_kernel, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
+            if (lp.tp.world > 1) launch_k(ln_mix_cluster_kernel<true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
+            else launch_k(ln_mix_cluster_kernel<false>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
         } else {
-            launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, lp, KC_LN, s, prof);
+            if (lp.tp.world > 1) launch_k(ln_mix_kernel<true>, dim3(rows), dim3(LN_THREADS), 0, lp, KC_LN, s, prof);
+            else launch_k(ln_mix_kernel<false>, dim3(rows), dim3(LN_THREADS), 0, lp, KC_LN, s, prof);
         }
     };
     const int wkv_slots = std::min(S, rows);
@@ -1268,17 +1283,24 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
                 memset(&q, 0, sizeof(q));
                 q.ln = ly.ln1;
                 q.ln.trace = tr_next(6);
+                q.ln.tp = site((fold && l > 0) ? 2 * l - 1 : -1);
                 q.W1 = ly.w1_raw; q.W2 = ly.w2_raw;
                 for (int j = 0; j < 5; ++j) { q.mu[j] = ly.mu5[j]; q.out[j] = a_x[j].p; }
                 q.lora = a_lora[0].p; q.lora_stride = (int)a_lora[0].halves_per_matrix;
                 q.Dm = info.time_mix_adapter;
                 q.gbar = pre_gbar;
                 launch_cluster = PRE_CLUSTER;
-                if (q.Dm == 32) launch_k(pre6_kernel<2>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
-                else launch_k(pre6_kernel<4>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+                const bool tq = q.ln.tp.world > 1;
+                if (q.Dm == 32) {
+                    if (tq) launch_k(pre6_kernel<2, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+                    else launch_k(pre6_kernel<2, false>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+                } else {
+                    if (tq) launch_k(pre6_kernel<4, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+                    else launch_k(pre6_kernel<4, false>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+                }
             }
         } else {
-            launch_ln(ly.ln1);
+            launch_ln(ly.ln1, l > 0 ? 2 * l - 1 : -1);
         }
         for (int gi = 0; gi < (int)ly.pre.size(); ++gi) {
             if (pre_skipped(ly, gi)) continue;
@@ -1304,12 +1326,17 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             }
         }
         gemm(ly.o);
-        if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
-        launch_ln(ly.ln2);
+        if (world > 1 && !fold) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
+        launch_ln(ly.ln2, 2 * l);
         for (auto& g : ly.ffn) gemm(g);
-        if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
+        if (world > 1 && !fold) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
     }
-    if (!(sk & 1)) launch_k(ln_out_kernel, dim3(rows), dim3(LN_THREADS), 0, lnout, KC_LN, s, prof);
+    if (!(sk & 1)) {
+        LnOutParams lo = lnout;
+        lo.tp = site(fold ? 2 * L - 1 : -1);
+        if (lo.tp.world > 1) launch_k(ln_out_kernel<true>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
+        else launch_k(ln_out_kernel<false>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
+    }
     if (MTR > 0 && !(sk & 16)) launch_gemm_chained(head, MTR);
     if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
 }
@@ -1374,6 +1401,7 @@ int b200rwkv_engine::fill_meta(int* m, const std::vector<int>& slots, const std:
         }
     }
     m[0] = T; m[1] = (int)slots.size(); m[2] = R;
+    m[4] = ++step_seq;        // identical on every rank (SPMD): epoch base of the folded rendezvous
     // WKV unit shape for the whole-step kernel: slots per (head, group) unit that minimises the
     // heaviest CTA's stage count under round-robin unit assignment
     {

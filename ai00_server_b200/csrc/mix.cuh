@@ -46,6 +46,7 @@ struct LnMixParams {
     float* commit_dst;      // [S, C] or null
     const float* commit_src;    // [T, C]
     unsigned long long* trace;  // profiling aid (null in production)
+    TpFold tp;                  // folded tensor-parallel rendezvous (world <= 1: none)
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -227,11 +228,13 @@ __device__ __forceinline__ void ln_mix_row(const LnMixParams& p, const int t, fl
     if (stamps && threadIdx.x == 0) stamps[6] = globaltimer_ns();
 }
 
+template <bool TPF = false>
 __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const __grid_constant__ LnMixParams p) {
     __shared__ float red[32];
     trace_stamp(p.trace, 0);
     pdl_launch_dependents();
     pdl_wait();
+    if (TPF) tp_rendezvous(p.tp);
     trace_stamp(p.trace, 1);
     const int t = blockIdx.x;
     if (t >= p.meta.T()) return;
@@ -320,6 +323,7 @@ struct LnOutParams {
     float* commit_dst;
     const float* commit_src;
     float* hidden_out;      // optional [T, C]: updated residual (debug / states endpoint)
+    TpFold tp;              // folded tensor-parallel rendezvous (world <= 1: none)
 };
 
 template <int NV, bool MEGA>
@@ -372,10 +376,12 @@ __device__ __forceinline__ void ln_out_row(const LnOutParams& p, const int t, fl
     else ln_out_row_nv<8, MEGA>(p, t, red);
 }
 
+template <bool TPF = false>
 __global__ void __launch_bounds__(LN_THREADS) ln_out_kernel(const __grid_constant__ LnOutParams p) {
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
+    if (TPF) tp_rendezvous(p.tp);
     const int t = blockIdx.x;
     if (t >= p.meta.T()) return;
     ln_out_row<false>(p, t, red);

@@ -218,6 +218,7 @@ __device__ __forceinline__ void pre_ln_slice(const LnMixParams& p, const int t, 
 }
 
 // LN stage alone (channel mix of every version, time mix of RWKV-5/7): 16 clusters x 8, no grid barrier
+template <bool TPF = false>
 __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __grid_constant__ LnMixParams p) {
     __shared__ float red[32];
     __shared__ float xch[2][2 * PRE_CLUSTER];
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __gri
     pdl_launch_dependents();
     const PreLnStatic<6> st = pre_ln_static<6>(p, t, rank);
     pdl_wait();
+    if (TPF) tp_rendezvous(p.tp);
     trace_stamp(p.trace, 1);
     if (t >= st.T) return;                // uniform over the cluster
     pre_ln_slice(p, t, cl, rank, st, red, xch);
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __gri
 }
 
 // KD = Dm / 16
-template <int KD>
+template <int KD, bool TPF = false>
 __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_constant__ Pre6Params p) {
     __shared__ float red[32];
     __shared__ float xch[2][2 * PRE_CLUSTER];
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
         mu3[i] = ok ? *reinterpret_cast<const float2*>(p.mu[j] + tc0[i] + tig * 2) : make_float2(0.f, 0.f);
     }
     pdl_wait();
+    if (TPF) tp_rendezvous(p.ln.tp);
     trace_stamp(tr, 1);
     cta_stamp(1);
     const int T = min(st.T, 16);
