@@ -399,7 +399,7 @@ struct b200rwkv_engine {
     bool fold_wd2 = false, lora_cc = false;
     int gemm_ring = 2;            // GemmCfg RING mode of the decode-shaped projection kernel
     bool tp_fold = false;         // experimental: rendezvous folded into the LN kernels (common.cuh TpFold), B200RWKV_TP_FOLD=1
-    TpFold tpf;                   // template of the per-launch descriptor (flags, seq, rank, world, nb)
+    TpFold tpf{};                 // template of the per-launch descriptor (flags, seq, rank, world, nb)
     int step_seq = 0;             // step sequence number uploaded as meta[4]
     bool gemm_fin = false;        // experimental designated-finisher stream-K (gemm.cuh), B200RWKV_FINISHER=1
     int sk_grid = 0;              // experimental: cap of the stream-K grid (B200RWKV_SK_GRID, e.g. 128 = 16 CTAs per GPC)
