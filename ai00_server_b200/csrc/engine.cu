@@ -401,6 +401,7 @@ struct b200rwkv_engine {
     bool tp_fold = false;         // experimental: rendezvous folded into the LN kernels (common.cuh TpFold), B200RWKV_TP_FOLD=1
     TpFold tpf{};                 // template of the per-launch descriptor (flags, seq, rank, world, nb)
     int step_seq = 0;             // step sequence number uploaded as meta[4]
+    int wkv_stream = 0;           // experimental streaming WKV (wkv.cuh wkv_stream_kernel): slot groups per head, B200RWKV_WKV_STREAM=G
     bool gemm_fin = false;        // experimental designated-finisher stream-K (gemm.cuh), B200RWKV_FINISHER=1
     int sk_grid = 0;              // experimental: cap of the stream-K grid (B200RWKV_SK_GRID, e.g. 128 = 16 CTAs per GPC)
     int prefetch_blocks = 16;     // L2 prefetch depth (32 KB blocks per CTA) into the next projection launch
@@ -637,10 +638,13 @@ void b200rwkv_engine::build(const StFile& st) {
     CK(cudaFuncSetAttribute(gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 1>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 2>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 2>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(wkv_stream_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CK(cudaFuncSetAttribute(wkv_stream_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     if (const char* v = getenv("B200RWKV_GEMM_HALF")) gemm_ring = atoi(v) != 0 ? 1 : 0;
     if (const char* v = getenv("B200RWKV_GEMM_RING")) gemm_ring = atoi(v);
     if (const char* v = getenv("B200RWKV_PREFETCH_BLOCKS")) prefetch_blocks = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_FINISHER")) gemm_fin = atoi(v) != 0;
+    if (const char* v = getenv("B200RWKV_WKV_STREAM")) wkv_stream = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_TP_FOLD")) tp_fold = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_SK_GRID")) sk_grid = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_LORA_CC")) lora_cc = atoi(v) != 0;
@@ -1319,6 +1323,12 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             const size_t wkv_smem = wkv_smem_bytes(info.version, fold_wd2, info.time_decay_adapter, rows);
             WkvParams wp = ly.wkv;
             wp.trace = tr_next(2);
+            const int G = std::max(wkv_stream, cdiv(wkv_slots, 2 * WKV_ST_MAXPOS));
+            if (wkv_stream > 0 && MT == 1 && info.version != 7 && G <= wkv_slots) {
+                const size_t sm_b = wkv_stream_smem_bytes(info.version, fold_wd2, info.time_decay_adapter, rows);
+                if (info.version == 6) launch_k(wkv_stream_kernel<6>, dim3(Hl, G), dim3(WKV_ST_THREADS), sm_b, wp, KC_WKV, s, prof, rows);
+                else launch_k(wkv_stream_kernel<5>, dim3(Hl, G), dim3(WKV_ST_THREADS), sm_b, wp, KC_WKV, s, prof, rows);
+            } else
             switch (info.version) {
                 case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), wkv_smem, wp, KC_WKV, s, prof, rows); break;
                 case 6: launch_k(wkv_kernel<6>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), wkv_smem, wp, KC_WKV, s, prof, rows); break;
