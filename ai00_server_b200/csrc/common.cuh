@@ -44,9 +44,25 @@ __device__ __forceinline__ __half f2h_sat(float v) {
     v = fminf(fmaxf(v, -65504.f), 65504.f);
     return __float2half_rn(v);
 }
+// Split operand (opt-in B200RWKV_SPLIT_ACT=1): a projection input v travels as two f16 numbers hi + lo = v
+// (to ~2^-22 relative); hi sits at token row t, lo at row t + 16 of the same A16 buffer (the second 16-token tile), the
+// projection multiplies both tiles and its epilogue adds the two accumulator tiles.
+__device__ __forceinline__ void split_h(const float v, __half& hi, __half& lo) {
+    hi = f2h_sat(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __halves2half2(f2h_sat(a), f2h_sat(b));
     return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void split_pack_h2(const float a, const float b, uint32_t& hi, uint32_t& lo) {
+    __half ah, al, bh, bl;
+    split_h(a, ah, al);
+    split_h(b, bh, bl);
+    __half2 h = __halves2half2(ah, bh), l = __halves2half2(al, bl);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
 // ---------------------------------------------------------------------------------------

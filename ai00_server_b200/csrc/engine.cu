@@ -401,6 +401,8 @@ struct b200rwkv_engine {
     bool tp_fold = false;         // experimental: rendezvous folded into the LN kernels (common.cuh TpFold), B200RWKV_TP_FOLD=1
     TpFold tpf{};                 // template of the per-launch descriptor (flags, seq, rank, world, nb)
     int step_seq = 0;             // step sequence number uploaded as meta[4]
+    bool split_on = false;        // split operands in effect (split_act and the cluster LN kernels are available)
+    bool split_act = false;       // experimental split (hi + lo f16) projection operands for decode-shaped steps, B200RWKV_SPLIT_ACT=1
     int wkv_stream = 0;           // experimental streaming WKV (wkv.cuh wkv_stream_kernel): slot groups per head, B200RWKV_WKV_STREAM=G
     bool gemm_fin = false;        // experimental designated-finisher stream-K (gemm.cuh), B200RWKV_FINISHER=1
     int sk_grid = 0;              // experimental: cap of the stream-K grid (B200RWKV_SK_GRID, e.g. 128 = 16 CTAs per GPC)
@@ -596,7 +598,8 @@ void b200rwkv_engine::launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, siz
 void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof) {
     switch (MT) {
         case 1:
-            if (gemm_ring == 1) launch_k(gemm_kernel<1, 1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            if (split_on) launch_k(gemm_kernel<2, 2, false, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<2, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            else if (gemm_ring == 1) launch_k(gemm_kernel<1, 1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             else if (gemm_fin) launch_k(gemm_kernel<1, 2, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             else if (gemm_ring == 2) launch_k(gemm_kernel<1, 2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             else launch_k(gemm_kernel<1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
@@ -638,6 +641,7 @@ void b200rwkv_engine::build(const StFile& st) {
     CK(cudaFuncSetAttribute(gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 1>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 2>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 2>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_kernel<2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 2>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(wkv_stream_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CK(cudaFuncSetAttribute(wkv_stream_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     if (const char* v = getenv("B200RWKV_GEMM_HALF")) gemm_ring = atoi(v) != 0 ? 1 : 0;
@@ -645,6 +649,7 @@ void b200rwkv_engine::build(const StFile& st) {
     if (const char* v = getenv("B200RWKV_PREFETCH_BLOCKS")) prefetch_blocks = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_FINISHER")) gemm_fin = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_WKV_STREAM")) wkv_stream = std::max(0, atoi(v));
+    if (const char* v = getenv("B200RWKV_SPLIT_ACT")) split_act = atoi(v) != 0 && world == 1;     // single GPU for now
     if (const char* v = getenv("B200RWKV_TP_FOLD")) tp_fold = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_SK_GRID")) sk_grid = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_LORA_CC")) lora_cc = atoi(v) != 0;
@@ -707,6 +712,7 @@ void b200rwkv_engine::build(const StFile& st) {
         pre_gbar = (unsigned*)dalloc(256, true);
         if (getenv("B200RWKV_STEP_TRACE")) d_step_trace = (unsigned long long*)dalloc((size_t)STEP_TRACE_MAX * STEP_TRACE_ROW * 8, true);
         ln_cluster_ok = ln_cluster && C % (4 * PRE_CLUSTER) == 0 && C / (4 * PRE_CLUSTER) <= PRE_THREADS;
+        split_on = split_act && ln_cluster_ok && !use_mega && !lora_cc;
     }
     const int S_att = pick_split(Cl, cdiv(C, GEMM_BN)), S_ffn = pick_split(Fl, cdiv(C, GEMM_BN));
     split_att = S_att; split_ffn = S_ffn;
@@ -1270,6 +1276,7 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
         if (ln_cluster_ok && MT == 1) {
             launch_cluster = PRE_CLUSTER;
             if (lp.tp.world > 1) launch_k(ln_mix_cluster_kernel<true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
+            else if (split_on) launch_k(ln_mix_cluster_kernel<false, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
             else launch_k(ln_mix_cluster_kernel<false>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
         } else {
             if (lp.tp.world > 1) launch_k(ln_mix_kernel<true>, dim3(rows), dim3(LN_THREADS), 0, lp, KC_LN, s, prof);
@@ -1290,12 +1297,15 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
                 q.ln.tp = site((fold && l > 0) ? 2 * l - 1 : -1);
                 q.W1 = ly.w1_raw; q.W2 = ly.w2_raw;
                 for (int j = 0; j < 5; ++j) { q.mu[j] = ly.mu5[j]; q.out[j] = a_x[j].p; }
-                q.lora = a_lora[0].p; q.lora_stride = (int)a_lora[0].halves_per_matrix;
+                q.lora = a_lora[0].p; q.lora_stride = (int)a_lora[0].halves_per_matrix; q.lora_kq = a_lora[0].kq;
                 q.Dm = info.time_mix_adapter;
                 q.gbar = pre_gbar;
                 launch_cluster = PRE_CLUSTER;
                 const bool tq = q.ln.tp.world > 1;
-                if (q.Dm == 32) {
+                if (split_on) {
+                    if (q.Dm == 32) launch_k(pre6_kernel<2, false, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+                    else launch_k(pre6_kernel<4, false, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+                } else if (q.Dm == 32) {
                     if (tq) launch_k(pre6_kernel<2, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
                     else launch_k(pre6_kernel<2, false>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
                 } else {
@@ -1324,10 +1334,17 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             WkvParams wp = ly.wkv;
             wp.trace = tr_next(2);
             const int G = std::max(wkv_stream, cdiv(wkv_slots, 2 * WKV_ST_MAXPOS));
-            if (wkv_stream > 0 && MT == 1 && info.version != 7 && G <= wkv_slots) {
+            if (wkv_stream > 0 && !split_on && MT == 1 && info.version != 7 && G <= wkv_slots) {
                 const size_t sm_b = wkv_stream_smem_bytes(info.version, fold_wd2, info.time_decay_adapter, rows);
                 if (info.version == 6) launch_k(wkv_stream_kernel<6>, dim3(Hl, G), dim3(WKV_ST_THREADS), sm_b, wp, KC_WKV, s, prof, rows);
                 else launch_k(wkv_stream_kernel<5>, dim3(Hl, G), dim3(WKV_ST_THREADS), sm_b, wp, KC_WKV, s, prof, rows);
+            } else if (split_on && MT == 1) {
+                const size_t sm_b = wkv_smem_bytes(info.version, fold_wd2, info.time_decay_adapter, rows, true);
+                switch (info.version) {
+                    case 5: launch_k(wkv_kernel<5, true>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
+                    case 6: launch_k(wkv_kernel<6, true>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
+                    default: launch_k(wkv_kernel<7, true>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
+                }
             } else
             switch (info.version) {
                 case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), wkv_smem, wp, KC_WKV, s, prof, rows); break;
@@ -1344,7 +1361,8 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
     if (!(sk & 1)) {
         LnOutParams lo = lnout;
         lo.tp = site(fold ? 2 * L - 1 : -1);
-        if (lo.tp.world > 1) launch_k(ln_out_kernel<true>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
+        if (split_on && MT == 1) launch_k(ln_out_kernel<false, true>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
+        else if (lo.tp.world > 1) launch_k(ln_out_kernel<true>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
         else launch_k(ln_out_kernel<false>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
     }
     if (MTR > 0 && !(sk & 16)) launch_gemm_chained(head, MTR);

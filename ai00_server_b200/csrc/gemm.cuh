@@ -204,7 +204,9 @@ __device__ __forceinline__ void gemm_mma_role(const GemmParams& p, const int b0,
 // registers while its own MMAs still run, then adds in the same fixed slot order as the default path (bit-identical
 // results).  This takes the atomic round trip and the dependent partial loads off the tail of stream-K launches
 // (profiles/r01_findings.md §7: +5..9 us on 148-CTA launches), which is what tensor-parallel shapes need.
-template <int MT, bool FIN = false>
+// SPLIT (opt-in B200RWKV_SPLIT_ACT=1, MT = 2): the two token tiles are the hi and lo halves of the SAME 16 tokens
+// (common.cuh split_h): the accumulator tiles are added before the epilogue and A16 outputs are written as hi / lo again.
+template <int MT, bool FIN = false, bool SPLIT = false>
 __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const int cta, const int G, const int b0, const int b1,
                                                    const uint32_t tfull_bar, const uint32_t tempty_bar, const uint32_t tmem_base,
                                                    unsigned& segcount, const int nrows, volatile int* s_last_p,
@@ -360,6 +362,12 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
             const float* const aux0 = sg.aux0;
             const float* const aux1 = sg.aux1;
             const float* const aux2 = sg.aux2;
+            if (SPLIT) {
+                static_assert(!SPLIT || MT == 2, "split operands use two token tiles");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[0][j] += v[MT - 1][j];
+            }
+            constexpr int MTE = SPLIT ? 1 : MT;        // token tiles the epilogue writes
             if (n < segN) {
                 const float bias = biasp ? biasp[n] : 0.f;
                 float lv[MT * 16];                     // dynamically indexed below -> local memory, rolled loop
@@ -367,10 +375,10 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
                 for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
                     for (int j = 0; j < 16; ++j) lv[mt * 16 + j] = v[mt][j];
-                const int mmax = min(nrows, MT * 16);
+                const int mmax = min(nrows, MTE * 16);
                 if (out_mode == OUT_F32) {
                     float* o = reinterpret_cast<float*>(outp) + n;
-                    if (MT == 1) {          // decode shape: straight from registers, all 16 stores in flight
+                    if (MTE == 1) {         // decode shape: straight from registers, all 16 stores in flight
 #pragma unroll
                         for (int m = 0; m < 16; ++m)
                             if (m < mmax) o[(size_t)m * ldo] = apply_act(v[0][m] + bias, act);
@@ -404,7 +412,14 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
                             if (m < mmax) {
                                 float y = apply_act(lv[m] + bias, act);
                                 if (out_mode == OUT_LERP_A16) y = x0[u] + x1[u] * (mu + y);
-                                base[a16_index(m, nn, ldo)] = f2h_sat(y);
+                                if (SPLIT) {
+                                    __half hi, lo;
+                                    split_h(y, hi, lo);
+                                    base[a16_index(m, nn, ldo)] = hi;
+                                    base[a16_index(m + 16, nn, ldo)] = lo;
+                                } else {
+                                    base[a16_index(m, nn, ldo)] = f2h_sat(y);
+                                }
                             }
                         }
                     }
@@ -418,7 +433,7 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
 // ---------------------------------------------------------------------------------------
 // stand-alone kernel: warps 0-3 epilogue, warp 4 MMA issuer (+ TMEM allocation), warp 5 TMA producer
 // ---------------------------------------------------------------------------------------
-template <int MT, int RING = 0, bool FIN = false>
+template <int MT, int RING = 0, bool FIN = false, bool SPLIT = false>
 __global__ void __launch_bounds__(GEMM_THREADS, RING == 1 ? 2 : 1) gemm_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<MT, RING>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -535,7 +550,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, RING == 1 ? 2 : 1) gemm_kernel(c
         pdl_wait();
         if (tid == 0) stamp(5);
         unsigned segcount = 0;
-        gemm_epilogue_role<MT, FIN>(p, cta, G, b0, b1, tfull_bar, tempty_bar, tmem_base, segcount, *p.nrows, &s_last, tr);
+        gemm_epilogue_role<MT, FIN, SPLIT>(p, cta, G, b0, b1, tfull_bar, tempty_bar, tmem_base, segcount, *p.nrows, &s_last, tr);
         if (tid == 0) stamp(6);
     }
     tc_fence_before();

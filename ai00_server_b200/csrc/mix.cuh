@@ -326,7 +326,7 @@ struct LnOutParams {
     TpFold tp;              // folded tensor-parallel rendezvous (world <= 1: none)
 };
 
-template <int NV, bool MEGA>
+template <int NV, bool MEGA, bool SPLIT = false>
 __device__ __forceinline__ void ln_out_row_nv(const LnOutParams& p, const int t, float* red) {
     const int C = p.C;
     const int slot = p.meta.tok_slot()[t];
@@ -359,24 +359,32 @@ __device__ __forceinline__ void ln_out_row_nv(const LnOutParams& p, const int t,
         const int c = 4 * (threadIdx.x + LN_THREADS * j);
         if (c < C) {
             const float4 y = ln_apply(a[j], mean, rstd, w[j], b[j]);
-            uint2 o;
-            o.x = pack_h2(y.x, y.y);
-            o.y = pack_h2(y.z, y.w);
-            *reinterpret_cast<uint2*>(p.head_in + a16_index(row, c, p.kq_tile)) = o;
+            if (SPLIT) {       // rows of the head operand are output rows (<= 16 in a decode-shaped step); lo halves in tile 1
+                uint2 hi, lo;
+                split_pack_h2(y.x, y.y, hi.x, lo.x);
+                split_pack_h2(y.z, y.w, hi.y, lo.y);
+                *reinterpret_cast<uint2*>(p.head_in + a16_index(row, c, p.kq_tile)) = hi;
+                *reinterpret_cast<uint2*>(p.head_in + a16_index(row + 16, c, p.kq_tile)) = lo;
+            } else {
+                uint2 o;
+                o.x = pack_h2(y.x, y.y);
+                o.y = pack_h2(y.z, y.w);
+                *reinterpret_cast<uint2*>(p.head_in + a16_index(row, c, p.kq_tile)) = o;
+            }
         }
     }
 }
 
-template <bool MEGA>
+template <bool MEGA, bool SPLIT = false>
 __device__ __forceinline__ void ln_out_row(const LnOutParams& p, const int t, float* red) {
     const int nv = (p.C + 4 * LN_THREADS - 1) / (4 * LN_THREADS);
-    if (nv <= 1) ln_out_row_nv<1, MEGA>(p, t, red);
-    else if (nv == 2) ln_out_row_nv<2, MEGA>(p, t, red);
-    else if (nv <= 4 || MEGA) ln_out_row_nv<4, MEGA>(p, t, red);      // the whole-step kernel caps C at 4096
-    else ln_out_row_nv<8, MEGA>(p, t, red);
+    if (nv <= 1) ln_out_row_nv<1, MEGA, SPLIT>(p, t, red);
+    else if (nv == 2) ln_out_row_nv<2, MEGA, SPLIT>(p, t, red);
+    else if (nv <= 4 || MEGA) ln_out_row_nv<4, MEGA, SPLIT>(p, t, red);      // the whole-step kernel caps C at 4096
+    else ln_out_row_nv<8, MEGA, SPLIT>(p, t, red);
 }
 
-template <bool TPF = false>
+template <bool TPF = false, bool SPLIT = false>
 __global__ void __launch_bounds__(LN_THREADS) ln_out_kernel(const __grid_constant__ LnOutParams p) {
     __shared__ float red[32];
     pdl_launch_dependents();
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(LN_THREADS) ln_out_kernel(const __grid_constan
     if (TPF) tp_rendezvous(p.tp);
     const int t = blockIdx.x;
     if (t >= p.meta.T()) return;
-    ln_out_row<false>(p, t, red);
+    ln_out_row<false, SPLIT>(p, t, red);
 }
 
 }  // namespace b200

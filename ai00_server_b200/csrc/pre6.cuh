@@ -44,6 +44,7 @@ struct Pre6Params {
     const float* mu[5];       // time_mix_{w,k,v,r,g}
     __half* lora;             // five A16 [16][Dm] matrices: tanh(W1 xxx)
     int lora_stride;          // halves between them
+    int lora_kq;              // k32 blocks per 16-token tile of those matrices (split operands: lo halves live in tile 1)
     __half* out[5];           // A16 [16][C] operands of decay-LoRA, K, V, R, G
     int Dm;
     unsigned* gbar;           // two arrival counters, 128 bytes apart
@@ -173,7 +174,7 @@ __device__ __forceinline__ PreLnStatic<NMIX> pre_ln_static(const LnMixParams& p,
 }
 
 // phase 1 for token t, channel slice `rank` (thread owns channels rank*C/8 + 4*tid .. +3)
-template <int NMIX>
+template <int NMIX, bool SPLIT = false>
 __device__ __forceinline__ void pre_ln_slice(const LnMixParams& p, const int t, cg::cluster_group& cl, const unsigned rank,
                                              const PreLnStatic<NMIX>& st, float* red, float (*xch)[2 * PRE_CLUSTER]) {
     const int C = p.C, Cs = C / PRE_CLUSTER;
@@ -209,16 +210,24 @@ __device__ __forceinline__ void pre_ln_slice(const LnMixParams& p, const int t, 
     for (int m = 0; m < NMIX; ++m) {
         if (m < p.n_mix) {
             const float4 mu = st.mu[m];
-            uint2 o;
-            o.x = pack_h2(a.x + sx.x * mu.x, a.y + sx.y * mu.y);
-            o.y = pack_h2(a.z + sx.z * mu.z, a.w + sx.w * mu.w);
-            *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t, c, p.kq_tile)) = o;
+            if (SPLIT) {
+                uint2 hi, lo;
+                split_pack_h2(a.x + sx.x * mu.x, a.y + sx.y * mu.y, hi.x, lo.x);
+                split_pack_h2(a.z + sx.z * mu.z, a.w + sx.w * mu.w, hi.y, lo.y);
+                *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t, c, p.kq_tile)) = hi;
+                *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t + 16, c, p.kq_tile)) = lo;
+            } else {
+                uint2 o;
+                o.x = pack_h2(a.x + sx.x * mu.x, a.y + sx.y * mu.y);
+                o.y = pack_h2(a.z + sx.z * mu.z, a.w + sx.w * mu.w);
+                *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t, c, p.kq_tile)) = o;
+            }
         }
     }
 }
 
 // LN stage alone (channel mix of every version, time mix of RWKV-5/7): 16 clusters x 8, no grid barrier
-template <bool TPF = false>
+template <bool TPF = false, bool SPLIT = false>
 __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __grid_constant__ LnMixParams p) {
     __shared__ float red[32];
     __shared__ float xch[2][2 * PRE_CLUSTER];
@@ -232,13 +241,13 @@ __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __gri
     if (TPF) tp_rendezvous(p.tp);
     trace_stamp(p.trace, 1);
     if (t >= st.T) return;                // uniform over the cluster
-    pre_ln_slice(p, t, cl, rank, st, red, xch);
+    pre_ln_slice<6, SPLIT>(p, t, cl, rank, st, red, xch);
     cl.sync();                            // no CTA leaves while a peer may still write into its exchange buffers
     trace_stamp(p.trace, 7);
 }
 
 // KD = Dm / 16
-template <int KD, bool TPF = false>
+template <int KD, bool TPF = false, bool SPLIT = false>
 __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_constant__ Pre6Params p) {
     __shared__ float red[32];
     __shared__ float xch[2][2 * PRE_CLUSTER];
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
     const int T = min(st.T, 16);
 
     // ---------------- phase 1: token g ----------------
-    if (g < T) pre_ln_slice(p.ln, g, cl, rank, st, red, xch);
+    if (g < T) pre_ln_slice<1, SPLIT>(p.ln, g, cl, rank, st, red, xch);
     trace_stamp(tr, 2);
     cta_stamp(2);
     pre_grid_barrier(cl, rank, p.gbar, p.gbar + 32, nullptr, 1);
@@ -322,23 +331,27 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
         for (int nt = 0; nt < PRE_NT2; ++nt)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-        const __half* xa = p.ln.mix_out[0];          // A16 [16][C], m tile 0
-        uint32_t af[PRE_KSW][4];
+        // split operands: the lo halves of the 16 tokens are the second 16-token tile of the same A16 buffer
 #pragma unroll
-        for (int i = 0; i < PRE_KSW; ++i) {
-            const int kstep = warp + 8 * i;
-            const int k = (int)rank * Cs + kstep * 16;
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(xa + ((size_t)(k >> 3) * 16 + grp) * 8 + tig * 2);
-            const bool ok = kstep < ksteps;
-            af[i][0] = ok ? __ldcg(src) : 0u;               // (t = grp,     k lo)
-            af[i][1] = ok ? __ldcg(src + 32) : 0u;          // (t = grp + 8, k lo)   +64 halves
-            af[i][2] = ok ? __ldcg(src + 64) : 0u;          // (t = grp,     k hi)   next 8-wide chunk
-            af[i][3] = ok ? __ldcg(src + 96) : 0u;          // (t = grp + 8, k hi)
+        for (int sp = 0; sp < (SPLIT ? 2 : 1); ++sp) {
+            const __half* xa = p.ln.mix_out[0] + (sp ? a16_index(16, 0, p.ln.kq_tile) : (size_t)0);      // A16 [16][C] tile
+            uint32_t af[PRE_KSW][4];
+#pragma unroll
+            for (int i = 0; i < PRE_KSW; ++i) {
+                const int kstep = warp + 8 * i;
+                const int k = (int)rank * Cs + kstep * 16;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(xa + ((size_t)(k >> 3) * 16 + grp) * 8 + tig * 2);
+                const bool ok = kstep < ksteps;
+                af[i][0] = ok ? __ldcg(src) : 0u;               // (t = grp,     k lo)
+                af[i][1] = ok ? __ldcg(src + 32) : 0u;          // (t = grp + 8, k lo)   +64 halves
+                af[i][2] = ok ? __ldcg(src + 64) : 0u;          // (t = grp,     k hi)   next 8-wide chunk
+                af[i][3] = ok ? __ldcg(src + 96) : 0u;          // (t = grp + 8, k hi)
+            }
+#pragma unroll
+            for (int i = 0; i < PRE_KSW; ++i)
+#pragma unroll
+                for (int nt = 0; nt < PRE_NT2; ++nt) mma_16816(acc[nt], af[i], w1f[i][nt][0], w1f[i][nt][1]);
         }
-#pragma unroll
-        for (int i = 0; i < PRE_KSW; ++i)
-#pragma unroll
-            for (int nt = 0; nt < PRE_NT2; ++nt) mma_16816(acc[nt], af[i], w1f[i][nt][0], w1f[i][nt][1]);
 #pragma unroll
         for (int nt = 0; nt < PRE_NT2; ++nt)
 #pragma unroll
@@ -366,7 +379,15 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
             const int n = g * RG + nrow;
             if (t < T && nrow < RG && n < NR) {
                 const int j = n / Dm, nn = n - j * Dm;
-                p.lora[(size_t)j * p.lora_stride + ((size_t)(nn >> 3) * 16 + t) * 8 + (nn & 7)] = f2h_sat(apply_act(s, ACT_TANH));
+                __half* dst = p.lora + (size_t)j * p.lora_stride;
+                if (SPLIT) {
+                    __half hi, lo;
+                    split_h(apply_act(s, ACT_TANH), hi, lo);
+                    dst[a16_index(t, nn, p.lora_kq)] = hi;
+                    dst[a16_index(t + 16, nn, p.lora_kq)] = lo;
+                } else {
+                    dst[((size_t)(nn >> 3) * 16 + t) * 8 + (nn & 7)] = f2h_sat(apply_act(s, ACT_TANH));
+                }
             }
         }
     }
@@ -378,6 +399,30 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
     {
         uint32_t af[PRE_TILES3][KD][4];
         float2 xx[PRE_TILES3][2], sx[PRE_TILES3][2];
+        float acc3[SPLIT ? PRE_TILES3 : 1][4];
+        if (SPLIT) {           // lo halves first (second 16-token tile of the LoRA matrices); the hi pass below adds to it
+#pragma unroll
+            for (int i = 0; i < PRE_TILES3; ++i)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc3[SPLIT ? i : 0][e] = 0.f;
+#pragma unroll
+            for (int i = 0; i < PRE_TILES3; ++i) {
+                const bool ok = tj[i] >= 0;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.lora + (size_t)(ok ? tj[i] : 0) * p.lora_stride +
+                                                                        a16_index(16, 0, p.lora_kq) + (size_t)grp * 8 + tig * 2);
+#pragma unroll
+                for (int ks = 0; ks < KD; ++ks) {
+                    af[i][ks][0] = ok ? __ldcg(src + ks * 128) : 0u;
+                    af[i][ks][1] = ok ? __ldcg(src + ks * 128 + 32) : 0u;
+                    af[i][ks][2] = ok ? __ldcg(src + ks * 128 + 64) : 0u;
+                    af[i][ks][3] = ok ? __ldcg(src + ks * 128 + 96) : 0u;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PRE_TILES3; ++i)
+#pragma unroll
+                for (int ks = 0; ks < KD; ++ks) mma_16816(acc3[SPLIT ? i : 0], af[i][ks], w2f[i][ks][0], w2f[i][ks][1]);
+        }
 #pragma unroll
         for (int i = 0; i < PRE_TILES3; ++i) {
             const bool ok = tj[i] >= 0;
@@ -402,6 +447,10 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
         for (int i = 0; i < PRE_TILES3; ++i) {
             if (tj[i] < 0) continue;
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (SPLIT) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[e] = acc3[SPLIT ? i : 0][e];
+            }
 #pragma unroll
             for (int ks = 0; ks < KD; ++ks) mma_16816(acc, af[i][ks], w2f[i][ks][0], w2f[i][ks][1]);
             __half* outp = p.out[tj[i]];
@@ -411,7 +460,14 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
                 if (t >= T) continue;
                 const float y0 = xx[i][h].x + sx[i][h].x * (mu3[i].x + acc[2 * h]);
                 const float y1 = xx[i][h].y + sx[i][h].y * (mu3[i].y + acc[2 * h + 1]);
-                *reinterpret_cast<uint32_t*>(outp + a16_index(t, tc0[i] + tig * 2, p.ln.kq_tile)) = pack_h2(y0, y1);
+                if (SPLIT) {
+                    uint32_t hi, lo;
+                    split_pack_h2(y0, y1, hi, lo);
+                    *reinterpret_cast<uint32_t*>(outp + a16_index(t, tc0[i] + tig * 2, p.ln.kq_tile)) = hi;
+                    *reinterpret_cast<uint32_t*>(outp + a16_index(t + 16, tc0[i] + tig * 2, p.ln.kq_tile)) = lo;
+                } else {
+                    *reinterpret_cast<uint32_t*>(outp + a16_index(t, tc0[i] + tig * 2, p.ln.kq_tile)) = pack_h2(y0, y1);
+                }
             }
         }
     }    trace_stamp(tr, 7);

@@ -86,7 +86,7 @@ __device__ __forceinline__ void wkv_sync() {
     if (SUB) asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory");
     else cta_sync<MEGA>();
 }
-template <int VER, bool MEGA, int KC = 4, int SUB = 0>
+template <int VER, bool MEGA, int KC = 4, int SUB = 0, bool SPLIT = false>
 __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const int t0, const int nt, float (&m)[4][KC],
                                          WkvShared& sm, const float* w_local, const int lt0, const float* pre = nullptr,
                                          const int pre_stride = 0, const float* statics = nullptr) {
@@ -218,8 +218,18 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
             const int gi = (lt0 + tt) * WKV_N + tid;
             y0 *= pre ? pre[3 * pre_stride + gi] : p.g[row + tid];
             y1 *= pre ? pre[3 * pre_stride + gi + 32] : p.g[row + tid + 32];
-            p.out[a16_index(t, ch + tid, p.kq_tile)] = f2h_sat(y0);
-            p.out[a16_index(t, ch + tid + 32, p.kq_tile)] = f2h_sat(y1);
+            if (SPLIT) {       // split operand of the output projection (common.cuh split_h): lo halves in the second token tile
+                __half h0, l0, h1, l1;
+                split_h(y0, h0, l0);
+                split_h(y1, h1, l1);
+                p.out[a16_index(t, ch + tid, p.kq_tile)] = h0;
+                p.out[a16_index(t, ch + tid + 32, p.kq_tile)] = h1;
+                p.out[a16_index(t + 16, ch + tid, p.kq_tile)] = l0;
+                p.out[a16_index(t + 16, ch + tid + 32, p.kq_tile)] = l1;
+            } else {
+                p.out[a16_index(t, ch + tid, p.kq_tile)] = f2h_sat(y0);
+                p.out[a16_index(t, ch + tid + 32, p.kq_tile)] = f2h_sat(y1);
+            }
         }
         wkv_sync<MEGA, SUB>();              // shared vectors are rewritten by the next token
     }
@@ -241,14 +251,15 @@ __host__ __device__ inline int wkv_stage_arrays(int ver, bool fold) { return ver
 
 // dynamic shared memory: [fold only: [Dd][64] halves (k-major slice of time_decay_w2) | [max tokens][64] floats (decays) |
 // [WKV_STAGE_TOK][Dd] halves | [2][64] floats] | staged rows [arrays][WKV_STAGE_TOK][64] floats | statics [3][64] floats
-__host__ __device__ inline size_t wkv_smem_bytes(int ver, bool fold, int Dd, int max_tokens) {
+__host__ __device__ inline size_t wkv_smem_bytes(int ver, bool fold, int Dd, int max_tokens, bool split = false) {
     size_t b = 0;
-    if (fold) b += (size_t)WKV_N * Dd * 2 + (size_t)max_tokens * WKV_N * 4 + ((((size_t)WKV_STAGE_TOK * Dd * 2) + 15) & ~(size_t)15) + 2 * WKV_N * 4;
+    if (fold) b += (size_t)WKV_N * Dd * 2 + (size_t)max_tokens * WKV_N * 4 + ((((size_t)WKV_STAGE_TOK * Dd * 2 * (split ? 2 : 1)) + 15) & ~(size_t)15) + 2 * WKV_N * 4;
     b += (size_t)wkv_stage_arrays(ver, fold) * WKV_STAGE_TOK * WKV_N * 4 + 3 * WKV_N * 4 + 64;
     return b;
 }
 
-template <int VER>
+// SPLIT (opt-in B200RWKV_SPLIT_ACT=1): the decay-LoRA input and the output are split operands (hi + lo f16 pairs).
+template <int VER, bool SPLIT = false>
 __global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_constant__ WkvParams p, const int max_tokens) {
     constexpr int KC = WKV_SA_KC, LANES = WKV_N / KC, NT = WKV_SA_THREADS;
     __shared__ WkvShared sm;
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_con
     if (fold) {
         wl = reinterpret_cast<float*>(dyn + (size_t)WKV_N * Dd * 2);
         ds = reinterpret_cast<__half*>(wl + (size_t)max_tokens * WKV_N);
-        part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ds) + ((((size_t)WKV_STAGE_TOK * Dd * 2) + 15) & ~(size_t)15));
+        part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ds) + ((((size_t)WKV_STAGE_TOK * Dd * 2 * (SPLIT ? 2 : 1)) + 15) & ~(size_t)15));
         dyn = reinterpret_cast<uint8_t*>(part + 2 * WKV_N);
     }
     const int na = wkv_stage_arrays(VER, fold);
@@ -343,6 +354,11 @@ __global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_con
             const int tt = i / Dd;
             ds[i] = p.d1[a16_index(t0 + tt, i - tt * Dd, p.d1_kq)];
         }
+        if (SPLIT)
+            for (int i = tid; i < ndd; i += NT) {
+                const int tt = i / Dd;
+                ds[WKV_STAGE_TOK * Dd + i] = p.d1[a16_index(t0 + tt + 16, i - tt * Dd, p.d1_kq)];
+            }
     }
 
     const float* w_local = nullptr;
@@ -355,12 +371,22 @@ __global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_con
             const __half* dt = staged ? ds + tt * Dd : ds;
             if (!staged) {
                 for (int k = tid; k < Dd; k += NT) ds[k] = p.d1[a16_index(t0 + tt, k, p.d1_kq)];
+                if (SPLIT)
+                    for (int k = tid; k < Dd; k += NT) ds[WKV_STAGE_TOK * Dd + k] = p.d1[a16_index(t0 + tt + 16, k, p.d1_kq)];
                 __syncthreads();
             }
             float acc0 = 0.f, acc1 = 0.f;
-            for (int k = kq0; k < kq1; k += 2) {
-                acc0 = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(dt[k]), acc0);
-                acc1 = fmaf(__half2float(wt[(k + 1) * WKV_N + c]), __half2float(dt[k + 1]), acc1);
+            if (SPLIT) {
+                const __half* dl = dt + WKV_STAGE_TOK * Dd;
+                for (int k = kq0; k < kq1; k += 2) {
+                    acc0 = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(dt[k]) + __half2float(dl[k]), acc0);
+                    acc1 = fmaf(__half2float(wt[(k + 1) * WKV_N + c]), __half2float(dt[k + 1]) + __half2float(dl[k + 1]), acc1);
+                }
+            } else {
+                for (int k = kq0; k < kq1; k += 2) {
+                    acc0 = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(dt[k]), acc0);
+                    acc1 = fmaf(__half2float(wt[(k + 1) * WKV_N + c]), __half2float(dt[k + 1]), acc1);
+                }
             }
             part[qk * WKV_N + c] = acc0 + acc1;
             __syncthreads();
@@ -369,7 +395,7 @@ __global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_con
         w_local = wl;
     }
     __syncthreads();
-    wkv_slot<VER, false, KC>(p, h, t0, nt, m, sm, w_local, 0, staged ? pre_s : nullptr, WKV_STAGE_TOK * WKV_N, statics);
+    wkv_slot<VER, false, KC, 0, SPLIT>(p, h, t0, nt, m, sm, w_local, 0, staged ? pre_s : nullptr, WKV_STAGE_TOK * WKV_N, statics);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
 #pragma unroll

@@ -402,3 +402,27 @@ def test_experimental_streaming_wkv(models, preset, groups):
     assert np.array_equal(outs[0][0], outs[1][0])
     for x, y in zip(outs[0][1], outs[1][1]):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.skipif(os.environ.get("B200RWKV_TEST_EXPERIMENTAL") != "1",
+                    reason="kernel paths written at the end of round 1 that have not run on hardware yet; opt-in")
+@pytest.mark.parametrize("preset", ["small6", "tiny5", "tiny7"])
+def test_experimental_split_operands_track_the_f32_oracle(models, preset):
+    """Split (hi + lo f16) projection operands (B200RWKV_SPLIT_ACT=1): no activation is rounded to f16 any
+    more, so decode must sit within f32 summation noise of the pure-f32 oracle -- an order of magnitude inside the 1e-3
+    budget and independent of depth."""
+    m, _, st = models(preset, mega=False, env={"B200RWKV_SPLIT_ACT": "1"})
+    orc = O.Oracle(O.parse_st(st), "f32")
+    rng = np.random.default_rng(8)
+    sts = [orc.state_init() for _ in range(3)]
+    for s in range(3):
+        m.state.load(m.state.init(), s)
+    worst = 0.0
+    for i in range(6):
+        toks = rng.integers(1, 500, size=3)
+        rows = m.infer_raw([0, 1, 2], [1, 1, 1], toks.tolist(), [capi.OPTION_LAST] * 3)
+        for s in range(3):
+            want, sts[s] = orc.run([int(toks[s])], sts[s])
+            worst = max(worst, rel_err(rows[s], want))
+            assert rows[s].argmax() == want.argmax()
+    assert worst <= 1e-4, worst
