@@ -422,7 +422,7 @@ struct b200rwkv_engine {
         step_trace_types[launches_last_step] = label;
         return d_step_trace + (size_t)STEP_TRACE_ROW * launches_last_step;
     }
-    void launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof);
+    void launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof, bool split = false);
     void enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* prof);
     void run_step(int MT, int MTR);
     int fill_meta(int* m, const std::vector<int>& slots, const std::vector<int>& counts, const std::vector<const uint32_t*>& toks,
@@ -595,10 +595,10 @@ void b200rwkv_engine::launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, siz
     ++launches_last_step;
 }
 
-void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof) {
+void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof, bool split) {
     switch (MT) {
         case 1:
-            if (split_on) launch_k(gemm_kernel<2, 2, false, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<2, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            if (split) launch_k(gemm_kernel<2, 2, false, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<2, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             else if (gemm_ring == 1) launch_k(gemm_kernel<1, 1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             else if (gemm_fin) launch_k(gemm_kernel<1, 2, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             else if (gemm_ring == 2) launch_k(gemm_kernel<1, 2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
@@ -1259,7 +1259,7 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             g2.p.next_grid = nx.grid;
             g2.p.prefetch_blocks = prefetch_blocks;
         }
-        launch_gemm(g2, mt, s, prof);
+        launch_gemm(g2, mt, s, prof, split_on && MT == 1);      // split operands only when the whole step is decode-shaped
     };
     auto gemm = [&](const GemmLaunch& g) {
         if (gemm_skipped(g)) return;
