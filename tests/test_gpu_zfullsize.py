@@ -80,3 +80,32 @@ def test_full_size_distance_to_the_oracle(big):
         floor = rel(a, b)                                   # oracle vs oracle: what f16 operand rounding alone does at this depth
         print(f"step {i}: engine vs C f16-contract {rel(rows, a):.2e}, vs C f32-contract {rel(rows, b):.2e}, oracle-vs-oracle {floor:.2e}")
         assert rel(rows, a) <= max(3e-2, 5 * floor) and rel(rows, b) <= max(3e-2, 5 * floor)
+
+
+def test_front_half_kernel_with_the_7b_lora_rank_matches_the_oracle():
+    """The RWKV-6 front-half kernel is templated on the ddlerp LoRA rank: 32 (every CI preset) and 64 (only the 7B shape).
+    A 4-layer model with rank 64 puts the 7B instantiation under the 1e-3 bound of the small-model tests."""
+    import dataclasses
+    shp = dataclasses.replace(synth.PRESETS["small6"], Dm=64, Dd=128)
+    st = synth.make_st(shp, 0)
+    os.environ["B200RWKV_MEGA"] = "0"
+    try:
+        m = runtime.Model(st, max_batch=4, token_chunk_size=32)
+    finally:
+        os.environ.pop("B200RWKV_MEGA", None)
+    try:
+        orc = O.Oracle(O.parse_st(st), "f16")
+        rng = np.random.default_rng(23)
+        counts = [1, 3, 1]
+        sts = [orc.state_init() for _ in counts]
+        for s in range(3):
+            m.state.load(m.state.init(), s)
+        for _ in range(4):
+            toks = [rng.integers(1, 2000, size=n).tolist() for n in counts]
+            rows = m.infer_raw([0, 1, 2], counts, sum(toks, []), [capi.OPTION_LAST] * 3)
+            for s in range(3):
+                want, sts[s] = orc.run(toks[s], sts[s])
+                err = float(np.abs(rows[s] - want).max() / np.abs(want).max())
+                assert err <= 1e-3 and rows[s].argmax() == want.argmax(), (s, err)
+    finally:
+        m.close()
