@@ -13,6 +13,10 @@ from oracle import rwkv_numpy as O
 pytestmark = pytest.mark.gpu
 PRESET = "v6-7b"
 
+if not os.path.exists(ref_c.LIB_PATH):
+    from ai00_server_b200 import build
+    build.build_oracle()
+
 
 @pytest.fixture(scope="module")
 def big():
