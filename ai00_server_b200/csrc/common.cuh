@@ -279,7 +279,7 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 // 65 per step.  Folded: every CTA of the consumer calls tp_rendezvous() right after griddepcontrol.wait (its own rank's
 // producer is complete and flushed): CTA 0 tells every peer "rank r reached site k of step seq", every CTA waits until all
 // peers said the same.  The epoch is seq * nb + k + 1 with seq uploaded with the step metadata, so nothing on the device
-// has to count and a captured graph replays correctly; flags are monotonic, compared with >=.
+// has to count and a captured graph replays correctly; flags only grow; compared modulo 2^32 ((int)(flag - epoch) >= 0), so the counters may wrap.
 // ---------------------------------------------------------------------------------------
 struct TpFold {
     unsigned* flags[8];     // flags[q]: rank q's flag array [8] (peer-mapped for q != rank); a region of its own
@@ -300,7 +300,7 @@ __device__ __forceinline__ void tp_rendezvous(const TpFold& f) {
         for (;;) {
             unsigned v;
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.flags[f.rank] + q) : "memory");
-            if (v >= e) break;
+            if ((int)(v - e) >= 0) break;          // wrap-safe comparison of 32-bit epochs
             sg_.poll(6u, (unsigned)q, e, v);
         }
         __threadfence_system();

@@ -135,6 +135,18 @@ public:
                 REQUIRE(b <= e && e <= data_len, B200RWKV_ERR_INVALID, "safetensors: tensor out of bounds: " + key);
                 t.data = base + b;
                 t.nbytes = e - b;
+                // byte length must equal dtype size x shape product (overflow-checked): every later size check trusts numel()
+                const size_t esz = dtype_size(t.dtype);
+                REQUIRE(esz > 0, B200RWKV_ERR_INVALID, "safetensors: unknown dtype '" + t.dtype + "' of " + key);
+                REQUIRE(t.shape.size() <= 8, B200RWKV_ERR_INVALID, "safetensors: too many dimensions: " + key);
+                uint64_t ne = 1;
+                for (int64_t d : t.shape) {
+                    REQUIRE(d >= 0 && (d == 0 || ne <= (uint64_t)1 << 40) && (uint64_t)d <= ((uint64_t)1 << 40), B200RWKV_ERR_INVALID,
+                            "safetensors: bad shape of " + key);
+                    ne *= (uint64_t)d;
+                }
+                REQUIRE(ne <= ((uint64_t)1 << 44) && ne * esz == (uint64_t)t.nbytes, B200RWKV_ERR_INVALID,
+                        "safetensors: byte length of " + key + " does not match dtype x shape");
                 tensors.emplace(std::move(key), std::move(t));
             }
             ws();
@@ -154,9 +166,25 @@ public:
         return *t;
     }
 
+    static size_t dtype_size(const std::string& d) {
+        if (d == "F16" || d == "BF16" || d == "I16" || d == "U16") return 2;
+        if (d == "F32" || d == "I32" || d == "U32") return 4;
+        if (d == "F64" || d == "I64" || d == "U64") return 8;
+        if (d == "I8" || d == "U8" || d == "BOOL" || d == "F8_E4M3" || d == "F8_E5M2") return 1;
+        return 0;
+    }
+    // dimension i of a tensor that must have exactly `rank` dimensions (0 = any rank > i)
+    static int64_t dim(const StTensor& t, size_t i, const std::string& name, size_t rank = 0) {
+        REQUIRE((rank == 0 || t.shape.size() == rank) && i < t.shape.size(), B200RWKV_ERR_INVALID, "unexpected rank of tensor " + name);
+        REQUIRE(t.shape[i] > 0 && t.shape[i] <= (int64_t)1 << 30, B200RWKV_ERR_INVALID, "bad dimension of tensor " + name);
+        return t.shape[i];
+    }
+    int64_t dim(const std::string& name, size_t i, size_t rank = 0) const { return dim(get(name), i, name, rank); }
+
 private:
     const char* s_;
     size_t n_, i_;
+    int depth_ = 0;
     char peek() { return i_ < n_ ? s_[i_] : '\0'; }
     void ws() { while (i_ < n_ && (s_[i_] == ' ' || s_[i_] == '\n' || s_[i_] == '\t' || s_[i_] == '\r')) ++i_; }
     void expect(char c) {
@@ -199,7 +227,14 @@ private:
         }
         return v;
     }
+    struct DepthGuard {
+        int& d;
+        explicit DepthGuard(int& d_) : d(d_) { ++d; }
+        ~DepthGuard() { --d; }
+    };
     void skip_value() {
+        DepthGuard dg(depth_);
+        REQUIRE(depth_ <= 64, B200RWKV_ERR_INVALID, "safetensors: header nested too deeply");
         ws();
         char c = peek();
         if (c == '"') { (void)str(); return; }
@@ -226,34 +261,29 @@ private:
 static b200rwkv_info derive_info(const StFile& st) {
     b200rwkv_info o;
     memset(&o, 0, sizeof(o));
-    const StTensor& emb = st.get("emb.weight");
-    REQUIRE(emb.shape.size() == 2, B200RWKV_ERR_INVALID, "emb.weight must be 2-D");
-    o.num_vocab = (int)emb.shape[0];
-    o.num_emb = (int)emb.shape[1];
+    o.num_vocab = (int)st.dim("emb.weight", 0, 2);
+    o.num_emb = (int)st.dim("emb.weight", 1, 2);
     int L = 0;
     while (st.find("blocks." + std::to_string(L) + ".ln1.weight")) ++L;
     REQUIRE(L > 0, B200RWKV_ERR_INVALID, "no blocks.*.ln1.weight tensors");
     o.num_layer = L;
-    o.num_hidden = (int)st.get("blocks.0.ffn.key.weight").shape[0];
+    o.num_hidden = (int)st.dim("blocks.0.ffn.key.weight", 0, 2);
     if (st.find("blocks.0.att.r_k")) {
         o.version = 7;
-        const auto& rk = st.get("blocks.0.att.r_k");
-        o.num_head = (int)rk.shape[0];
-        o.head_size = (int)rk.shape[1];
-        o.time_decay_adapter = (int)st.get("blocks.0.att.w1").shape[0];
+        o.num_head = (int)st.dim("blocks.0.att.r_k", 0, 2);
+        o.head_size = (int)st.dim("blocks.0.att.r_k", 1, 2);
+        o.time_decay_adapter = (int)st.dim("blocks.0.att.w1", 0, 2);
     } else if (st.find("blocks.0.att.time_mix_w1")) {
         o.version = 6;
-        const auto& tf = st.get("blocks.0.att.time_first");
-        o.num_head = (int)tf.shape[0];
-        o.head_size = (int)tf.shape[1];
-        o.time_mix_adapter = (int)st.get("blocks.0.att.time_mix_w1").shape[0] / 5;
-        o.time_decay_adapter = (int)st.get("blocks.0.att.time_decay_w1").shape[0];
+        o.num_head = (int)st.dim("blocks.0.att.time_first", 0, 2);
+        o.head_size = (int)st.dim("blocks.0.att.time_first", 1, 2);
+        o.time_mix_adapter = (int)st.dim("blocks.0.att.time_mix_w1", 0, 2) / 5;
+        o.time_decay_adapter = (int)st.dim("blocks.0.att.time_decay_w1", 0, 2);
     } else if (st.find("blocks.0.att.ln_x.weight") && st.find("blocks.0.att.gate.weight")) {
         o.version = 5;
-        const auto& tf = st.get("blocks.0.att.time_first");
-        REQUIRE(tf.shape.size() == 2, B200RWKV_ERR_UNSUPPORTED, "v5.0 (scalar time_first) is not supported");
-        o.num_head = (int)tf.shape[0];
-        o.head_size = (int)tf.shape[1];
+        REQUIRE(st.get("blocks.0.att.time_first").shape.size() == 2, B200RWKV_ERR_UNSUPPORTED, "v5.0 (scalar time_first) is not supported");
+        o.num_head = (int)st.dim("blocks.0.att.time_first", 0, 2);
+        o.head_size = (int)st.dim("blocks.0.att.time_first", 1, 2);
     } else {
         throw Error(B200RWKV_ERR_UNSUPPORTED, "unsupported model version (RWKV v5.1/5.2, v6, v7 are supported)");
     }
@@ -316,7 +346,7 @@ using namespace b200;
 struct b200rwkv_engine {
     b200rwkv_info info;
     int dev = 0, rank = 0, world = 1, num_sms = 148;
-    int S = 0, chunk = 0, maxT = 64;
+    int S = 0, chunk = 0, maxT = 64, precision = 0;
     int L = 0, C = 0, F = 0, V = 0, H = 0, N = 64, Cl = 0, Hl = 0, Fl = 0, Vl = 0;
     bool use_graph = true, use_pdl = true;
     bool use_mega = false, mega_ok = false;   // whole-step kernel is opt-in (B200RWKV_MEGA=1): see DESIGN.md, measured slower in round 1
@@ -400,7 +430,7 @@ struct b200rwkv_engine {
     int gemm_ring = 2;            // GemmCfg RING mode of the decode-shaped projection kernel
     bool tp_fold = false;         // experimental: rendezvous folded into the LN kernels (common.cuh TpFold), B200RWKV_TP_FOLD=1
     TpFold tpf{};                 // template of the per-launch descriptor (flags, seq, rank, world, nb)
-    int step_seq = 0;             // step sequence number uploaded as meta[4]
+    unsigned step_seq = 0;        // step sequence number uploaded as meta[4] (wraps; the rendezvous compares modulo 2^32)
     bool split_on = false;        // split operands in effect (split_act and the cluster LN kernels are available)
     bool split_act = false;       // experimental split (hi + lo f16) projection operands for decode-shaped steps, B200RWKV_SPLIT_ACT=1
     int wkv_stream = 0;           // experimental streaming WKV (wkv.cuh wkv_stream_kernel): slot groups per head, B200RWKV_WKV_STREAM=G
@@ -438,10 +468,25 @@ b200rwkv_engine::~b200rwkv_engine() {
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (auto& kv : snaps) cudaFree(kv.second.buf);
     for (void* p : allocs) cudaFree(p);
+    if (d_tmp) cudaFree(d_tmp);          // only still set when build() threw
+    if (sm_in) cudaFree(sm_in);
+    if (sm_out) cudaFree(sm_out);
     if (h_meta) cudaFreeHost(h_meta);
     if (stream) cudaStreamDestroy(stream);
     if (sm_stream) cudaStreamDestroy(sm_stream);
 }
+
+// scratch device allocation released on every exit path
+struct DevTmp {
+    void* p = nullptr;
+    explicit DevTmp(size_t bytes) {
+        cudaError_t e_ = cudaMalloc(&p, std::max<size_t>(bytes, 16));
+        if (e_ != cudaSuccess) throw Error(B200RWKV_ERR_CUDA, std::string("cudaMalloc (scratch): ") + cudaGetErrorString(e_));
+    }
+    ~DevTmp() { if (p) cudaFree(p); }
+    DevTmp(const DevTmp&) = delete;
+    DevTmp& operator=(const DevTmp&) = delete;
+};
 
 void* b200rwkv_engine::dalloc(size_t bytes, bool zero) {
     void* p = nullptr;
@@ -465,13 +510,11 @@ float* b200rwkv_engine::vec_f32(const StFile& st, const std::string& name, size_
     const StTensor& t = st.get(name);
     REQUIRE((size_t)t.numel() >= off + count, B200RWKV_ERR_INVALID, "tensor too small: " + name);
     float* d = (float*)dalloc(count * 4, false);
-    __half* tmp = nullptr;
-    CK(cudaMalloc(&tmp, count * 2));
-    CK(cudaMemcpy(tmp, t.data + off * 2, count * 2, cudaMemcpyHostToDevice));
-    f16_to_f32_kernel<<<cdiv((int)count, 256), 256>>>(tmp, d, count, scale, bias);
+    DevTmp tmp(count * 2);
+    CK(cudaMemcpy(tmp.p, t.data + off * 2, count * 2, cudaMemcpyHostToDevice));
+    f16_to_f32_kernel<<<cdiv((int)count, 256), 256>>>((const __half*)tmp.p, d, count, scale, bias);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    CK(cudaFree(tmp));
     return d;
 }
 
@@ -518,7 +561,7 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
             REQUIRE(t.shape.size() == 3, B200RWKV_ERR_INVALID, "internal: slice of non-3D tensor");
             ld = (int)t.shape[2];
             src += (size_t)d.slice * t.shape[1] * t.shape[2];
-            REQUIRE(d.n0 + d.N <= t.shape[1] && d.k0 + d.K <= t.shape[2], B200RWKV_ERR_INVALID, "weight shape mismatch");
+            REQUIRE(d.slice < t.shape[0] && d.n0 + d.N <= t.shape[1] && d.k0 + d.K <= t.shape[2], B200RWKV_ERR_INVALID, "weight shape mismatch");
         } else {
             REQUIRE(t.shape.size() == 2, B200RWKV_ERR_INVALID, "internal: expected 2-D weight");
             ld = (int)t.shape[1];
@@ -650,6 +693,7 @@ void b200rwkv_engine::build(const StFile& st) {
     if (const char* v = getenv("B200RWKV_FINISHER")) gemm_fin = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_WKV_STREAM")) wkv_stream = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_SPLIT_ACT")) split_act = atoi(v) != 0 && world == 1;     // single GPU for now
+    if (precision == 1) split_act = true;         // f32-activation mode (web-rwkv `Bundle::<f32>`): no activation is rounded to f16
     if (const char* v = getenv("B200RWKV_TP_FOLD")) tp_fold = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_SK_GRID")) sk_grid = std::max(0, atoi(v));
     if (const char* v = getenv("B200RWKV_LORA_CC")) lora_cc = atoi(v) != 0;
@@ -713,6 +757,7 @@ void b200rwkv_engine::build(const StFile& st) {
         if (getenv("B200RWKV_STEP_TRACE")) d_step_trace = (unsigned long long*)dalloc((size_t)STEP_TRACE_MAX * STEP_TRACE_ROW * 8, true);
         ln_cluster_ok = ln_cluster && C % (4 * PRE_CLUSTER) == 0 && C / (4 * PRE_CLUSTER) <= PRE_THREADS;
         split_on = split_act && ln_cluster_ok && !use_mega && !lora_cc;
+        REQUIRE(precision != 1 || split_on, B200RWKV_ERR_UNSUPPORTED, "precision 1 needs num_emb to be a multiple of 32 and <= 8192");
     }
     const int S_att = pick_split(Cl, cdiv(C, GEMM_BN)), S_ffn = pick_split(Fl, cdiv(C, GEMM_BN));
     split_att = S_att; split_ffn = S_ffn;
@@ -828,6 +873,15 @@ void b200rwkv_engine::build(const StFile& st) {
                 }
                 ly.pre.push_back(make_launch(sv));
             }
+            {   // the raw copies below are indexed with these exact shapes
+                const StTensor& w1 = st.get(a + "time_mix_w1");
+                const StTensor& w2 = st.get(a + "time_mix_w2");
+                const StTensor& d2 = st.get(a + "time_decay_w2");
+                REQUIRE(w1.shape.size() == 2 && w1.shape[0] == 5 * Dm && w1.shape[1] == C, B200RWKV_ERR_INVALID, "time_mix_w1 must be [5*Dm, C]");
+                REQUIRE(w2.shape.size() == 3 && w2.shape[0] == 5 && w2.shape[1] == C && w2.shape[2] == Dm, B200RWKV_ERR_INVALID,
+                        "time_mix_w2 must be [5, C, Dm]");
+                REQUIRE(d2.shape.size() == 2 && d2.shape[0] == C && d2.shape[1] == Dd, B200RWKV_ERR_INVALID, "time_decay_w2 must be [C, Dd]");
+            }
             if (fused_pre && (Dm == 32 || Dm == 64) && C % 128 == 0 && C <= PRE_MAX_C) {
                 auto upload_raw = [&](const StTensor& t) {
                     __half* d = (__half*)dalloc(t.nbytes, false);
@@ -895,21 +949,19 @@ void b200rwkv_engine::build(const StFile& st) {
                 const StTensor& td = st.get(a + "time_decay");
                 REQUIRE(td.numel() == C, B200RWKV_ERR_UNSUPPORTED, "v5 time_decay must be [H, N]");
                 float* d = (float*)dalloc((size_t)Cl * 4, false);
-                __half* tmp = nullptr;
-                CK(cudaMalloc(&tmp, (size_t)Cl * 2));
-                CK(cudaMemcpy(tmp, td.data + (size_t)c0 * 2, (size_t)Cl * 2, cudaMemcpyHostToDevice));
-                decay_table_kernel<<<cdiv(Cl, 256), 256>>>(tmp, d, Cl);
+                DevTmp tmp((size_t)Cl * 2);
+                CK(cudaMemcpy(tmp.p, td.data + (size_t)c0 * 2, (size_t)Cl * 2, cudaMemcpyHostToDevice));
+                decay_table_kernel<<<cdiv(Cl, 256), 256>>>((const __half*)tmp.p, d, Cl);
                 CK(cudaDeviceSynchronize());
-                CK(cudaFree(tmp));
                 wk.w_static = d;
             }
             wk.u = vec_f32(st, a + "time_first", c0, Cl);
         } else {
             // v7: six static lerps r,w,k,v,a,g -> a_x[0..5]
             static const char* names[6] = {"x_r", "x_w", "x_k", "x_v", "x_a", "x_g"};
-            const int Dw = (int)st.get(a + "w1").shape[0], Da = (int)st.get(a + "a1").shape[0], Dg = (int)st.get(a + "g1").shape[0];
-            const StTensor* v1t = st.find(L > 1 ? "blocks.1.att.v1" : "blocks.0.att.v1");
-            const int Dv = v1t ? (int)v1t->shape[0] : 32;
+            const int Dw = (int)st.dim(a + "w1", 0, 2), Da = (int)st.dim(a + "a1", 0, 2), Dg = (int)st.dim(a + "g1", 0, 2);
+            const std::string v1n = L > 1 ? "blocks.1.att.v1" : "blocks.0.att.v1";
+            const int Dv = st.find(v1n) ? (int)st.dim(v1n, 0, 2) : 32;
             if (l == 0) {
                 a_lora[0] = a16_alloc(Dw); a_lora[1] = a16_alloc(Da); a_lora[2] = a16_alloc(Dv); a_lora[3] = a16_alloc(Dg);
             }
@@ -1429,7 +1481,7 @@ int b200rwkv_engine::fill_meta(int* m, const std::vector<int>& slots, const std:
         }
     }
     m[0] = T; m[1] = (int)slots.size(); m[2] = R;
-    m[4] = ++step_seq;        // identical on every rank (SPMD): epoch base of the folded rendezvous
+    m[4] = (int)++step_seq;   // identical on every rank (SPMD): epoch base of the folded rendezvous
     // WKV unit shape for the whole-step kernel: slots per (head, group) unit that minimises the
     // heaviest CTA's stage count under round-robin unit assignment
     {
@@ -1473,10 +1525,13 @@ void b200rwkv_engine::infer(int nslot, const int32_t* slot, const int32_t* ntok,
         total_tok += (size_t)ntok[i];
     }
     REQUIRE(total_tok == 0 || tokens, B200RWKV_ERR_INVALID, "infer: null tokens");
+    for (size_t i = 0; i < total_tok; ++i)
+        REQUIRE(tokens[i] < (uint32_t)V, B200RWKV_ERR_INVALID, "infer: token id " + std::to_string(tokens[i]) + " is outside the vocabulary");
     const bool want_logits = (rank == 0);          // tensor parallel: rank 0 gathers all vocabulary shards
     REQUIRE(!want_logits || total_rows * (size_t)V <= cap || total_rows == 0, B200RWKV_ERR_INVALID, "infer: logits buffer too small");
     REQUIRE(!want_logits || total_rows == 0 || logits_out, B200RWKV_ERR_INVALID, "infer: null logits buffer");
-    const int step_cap = std::min(chunk, maxT);
+    // f32-activation mode runs every step decode-shaped (<= 16 tokens): the split-operand kernels are the 16-token ones
+    const int step_cap = std::min(chunk, split_on ? 16 : maxT);
     // cursor over entries
     std::vector<size_t> base(nslot + 1, 0);
     for (int i = 0; i < nslot; ++i) base[i + 1] = base[i] + (size_t)ntok[i];
@@ -1566,7 +1621,8 @@ int32_t b200rwkv_create_tp(const uint8_t* st, size_t len, int32_t device, int32_
     API_BEGIN((b200rwkv_engine*)nullptr)
     REQUIRE(out, B200RWKV_ERR_INVALID, "null out");
     *out = nullptr;
-    REQUIRE(precision == 0, B200RWKV_ERR_UNSUPPORTED, "only fp16 weights (precision 0) are supported");
+    REQUIRE(precision == 0 || precision == 1, B200RWKV_ERR_INVALID, "precision must be 0 (fp16) or 1 (fp32)");
+    REQUIRE(precision == 0 || world == 1, B200RWKV_ERR_UNSUPPORTED, "precision 1 (f32 activations) is single-GPU only");
     REQUIRE(max_batch >= 1 && max_batch <= 1024, B200RWKV_ERR_INVALID, "max_batch out of range");
     REQUIRE(token_chunk_size >= 1, B200RWKV_ERR_INVALID, "token_chunk_size must be >= 1");
     REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, B200RWKV_ERR_INVALID, "bad rank/world");
@@ -1589,7 +1645,7 @@ int32_t b200rwkv_create_tp(const uint8_t* st, size_t len, int32_t device, int32_
     StFile f(st, len);
     std::unique_ptr<b200rwkv_engine> e(new b200rwkv_engine());
     e->dev = device; e->rank = rank; e->world = world; e->num_sms = prop.multiProcessorCount;
-    e->S = max_batch; e->chunk = token_chunk_size;
+    e->S = max_batch; e->chunk = token_chunk_size; e->precision = precision;
     if (const char* v = getenv("B200RWKV_GRAPH")) e->use_graph = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_PDL")) e->use_pdl = atoi(v) != 0;
     if (const char* v = getenv("B200RWKV_SKIP")) e->skip_mask = atoi(v);
@@ -1832,6 +1888,8 @@ static void build_decode_metas(b200rwkv_engine* e, int nslot, const int32_t* slo
     all.assign((size_t)nsteps * e->meta_ints, 0);
     std::vector<int> s_slots(slot, slot + nslot), s_counts(nslot, 1), s_out(nslot, 1);
     std::vector<const uint32_t*> s_toks(nslot);
+    for (size_t i = 0; i < (size_t)nsteps * nslot; ++i)
+        REQUIRE(tokens[i] < (uint32_t)e->V, B200RWKV_ERR_INVALID, "token id outside the vocabulary");
     for (int st = 0; st < nsteps; ++st) {
         for (int i = 0; i < nslot; ++i) s_toks[i] = tokens + (size_t)st * nslot + i;
         int R = 0;

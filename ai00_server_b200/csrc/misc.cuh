@@ -101,7 +101,7 @@ __device__ __forceinline__ void tp_barrier(const TpBar& b, const int lane) {
         __threadfence_system();
         st_release_sys(b.flags[lane] + b.rank, e);
         SpinGuard sg_;
-        while (ld_acquire_sys(b.flags[b.rank] + lane) < e) sg_.poll(5u, (unsigned)lane, e, (unsigned)b.rank);
+        while ((int)(ld_acquire_sys(b.flags[b.rank] + lane) - e) < 0) sg_.poll(5u, (unsigned)lane, e, (unsigned)b.rank);   // wrap-safe: epochs are 32-bit and only grow
     }
     __syncwarp();
     __threadfence_system();

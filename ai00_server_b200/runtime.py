@@ -154,7 +154,9 @@ class Model:
     `TokioRuntime::new(bundle)`, lib.rs:484-497)."""
 
     def __init__(self, st: np.ndarray, max_batch: int = 8, token_chunk_size: int = 128, device: int = 0,
-                 precision: int = 0, rank: int = 0, world: int = 1):
+                 precision: int = 0, rank: int = 0, world: int = 1, exact: bool = False):
+        if exact:
+            precision = 1          # `Bundle::<f32>`: f32-exact activations (split hi + lo f16 operands)
         st = np.ascontiguousarray(st, dtype=np.uint8)
         h = C.c_void_p()
         L = capi.lib()

@@ -32,10 +32,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "decode tokens/s RWKV-6-World-7B fp16 batch=16"
+# BASELINE.json: the headline metric is quoted on configs[2] (7B, batch 16); configs[1] and [3] are the secondary lines
+MODEL_NAMES = {"v6-7b": "RWKV-6-World-7B", "v6-3b": "RWKV-6-World-3B", "v6-1b6": "RWKV-6-World-1.6B", "v7-2b9": "RWKV-7-World-2.9B"}
 PRESET = os.environ.get("B200RWKV_BENCH_PRESET", "v6-7b")
 BATCH = int(os.environ.get("B200RWKV_BENCH_BATCH", "16"))
 PROMPT = int(os.environ.get("B200RWKV_BENCH_PROMPT", "128"))
+
+
+def metric_name(preset: str, batch: int) -> str:
+    return f"decode tokens/s {MODEL_NAMES.get(preset, preset)} fp16 batch={batch}"
 
 
 def read_peaks():
@@ -102,23 +107,19 @@ def make_tokens(n_steps: int, batch: int, vocab: int):
 
 
 def host_threads() -> int:
-    """Threads the CPU arm should use: physical cores inside this process' affinity mask and cgroup CPU quota.
-    (Measured on the GPU box: 128 OpenMP threads on its 64 cores run the same step 18x slower than 64.)"""
-    try:                       # torch sizes its intra-op pool to the physical cores it may use; the default arm's CPU leg
-        import torch           # runs with exactly this count (64 on the GPU box), so both arms agree
-        n = int(torch.get_num_threads())
-        if n >= 1:
-            return n
-    except Exception:
-        pass
+    """Threads the CPU arms use: the physical cores inside this process' affinity mask and cgroup CPU quota (measured on
+    the GPU box: 128 OpenMP threads on its 64 cores run the same step 18x slower than 64).  Never taken from
+    OMP_NUM_THREADS: torchrun exports OMP_NUM_THREADS=1 to its workers."""
+    if os.environ.get("B200RWKV_CPU_THREADS"):
+        return max(1, int(os.environ["B200RWKV_CPU_THREADS"]))
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
         import psutil
-        phys = psutil.cpu_count(logical=False)
-        if phys:
-            n = min(n, phys)
+        phys, logical = psutil.cpu_count(logical=False), psutil.cpu_count(logical=True)
+        if phys and logical and logical > phys:
+            n = max(1, min(phys, n * phys // logical))
     except Exception:
-        n = max(1, n // 2)
+        pass
     try:
         quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
         if quota != "max":
@@ -128,35 +129,45 @@ def host_threads() -> int:
     return max(1, n)
 
 
-def cpu_arm(weights, batch: int, steps: int, warmup: int, toks_bt: np.ndarray):
-    """Times the C/OpenMP oracle on the host cores: `steps` decode steps of the same workload."""
-    if "OMP_NUM_THREADS" not in os.environ:        # must be set before libgomp is loaded
-        os.environ["OMP_NUM_THREADS"] = str(host_threads())
+def cpu_arm(weights, batch: int, steps: int, warmup: int, toks_bt: np.ndarray, budget_s: float = 1e9):
+    """Times the C/OpenMP oracle on the host cores: up to `steps` decode steps of the same workload (stops early once
+    `budget_s` seconds of timed work are spent).  Returns tokens/s, ms/step, threads, steps timed."""
     os.environ.setdefault("OMP_PROC_BIND", "false")
     from ai00_server_b200 import build
     from oracle import ref_c
     if not os.path.exists(ref_c.LIB_PATH):
         build.build_oracle()
     rc = ref_c.RefC(weights, "f16")
+    rc.set_num_threads(host_threads())             # explicit: the inherited OMP_NUM_THREADS is not ours (torchrun sets 1)
     st = rc.state_init(batch)
     for i in range(warmup):
         rc.decode_step(toks_bt[:, i % toks_bt.shape[1]], st)
     t0 = time.perf_counter()
+    done = 0
     for i in range(steps):
         rc.decode_step(toks_bt[:, (warmup + i) % toks_bt.shape[1]], st)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3, rc.num_threads()
+    return batch * done / dt, dt / done * 1e3, rc.num_threads(), done
 
 
 def main():
+    global PRESET, BATCH
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=int(os.environ.get("B200RWKV_BENCH_CPU_STEPS", "6")))
+    ap.add_argument("--preset", default=PRESET, help="model shape: v6-7b (headline), v6-3b, v7-2b9, v6-1b6 (BASELINE.json configs)")
+    ap.add_argument("--batch", type=int, default=BATCH, help="concurrent slots, one token per slot per step")
+    ap.add_argument("--exact", action="store_true", help="precision 1: f32-exact activations (split hi+lo operands)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    PRESET, BATCH = args.preset, args.batch
+    METRIC = metric_name(PRESET, BATCH)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -167,6 +178,7 @@ def main():
     shape = synth.PRESETS[PRESET]
     config = {"workload": f"{PRESET} decode, batch {BATCH} slots x 1 token/step, {PROMPT}-token synthetic prompt per slot",
               "preset": PRESET, "batch": BATCH, "prompt_tokens": PROMPT, "parallelism": f"tp{world}",
+              "activations": "f32-exact (split f16 hi+lo operands)" if args.exact else "f16 operands",
               "l2": "inputs larger than L2 (14.7 GB of weights streamed per step vs 126 MB L2), no flush"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -175,16 +187,15 @@ def main():
             return
         st = synth.make_st(shape, 0)
         w = O.parse_st(st)
-        steps = max(1, min(args.steps, 8))
-        warm = 1
-        toks = make_tokens(steps + warm, BATCH, shape.V)
-        tps, ms, threads = cpu_arm(w, BATCH, steps, warm, toks)
+        warm = max(1, min(args.warmup, 2))
+        toks = make_tokens(args.steps + warm, BATCH, shape.V)
+        tps, ms, threads, steps = cpu_arm(w, BATCH, args.steps, warm, toks, budget_s=150.0)
         line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": "tokens/s", "n_gpus": args.gpus,
                 "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                 "sample": f"{steps} decode steps of the full workload (requested {args.steps}), C/OpenMP oracle; "
-                                           "reference web-rwkv/lavapipe path unbuildable here"},
+                                 "sample": f"{steps} decode steps of the full workload (requested {args.steps}; bounded to ~150 s), "
+                                           "C/OpenMP oracle on the physical host cores; reference web-rwkv/lavapipe path unbuildable here"},
                 "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -200,7 +211,7 @@ def main():
 
     t_build = time.perf_counter()
     st = synth.make_st(shape, 0)
-    model = runtime.Model(st, max_batch=BATCH, token_chunk_size=64, device=dev, rank=rank, world=world)
+    model = runtime.Model(st, max_batch=BATCH, token_chunk_size=64, device=dev, rank=rank, world=world, exact=args.exact)
     if world > 1:
         from ai00_server_b200 import tp
         tp.connect(model)
@@ -281,7 +292,7 @@ def main():
     alg_bytes = synth.algorithmic_bytes_per_step(shape, BATCH) / world
     traffic = None       # DRAM bytes of the same launches from the committed ncu capture (N = 1 capture of this workload)
     tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if world == 1 and PRESET == "v6-7b" and os.path.exists(tpath):
+    if world == 1 and PRESET == "v6-7b" and BATCH == 16 and os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic = tj["layers"] * sum(x["dram_bytes"] for x in tj["per_layer_gemm_launches"]) + tj["head"]["algorithmic_weight_bytes"]
     roofline = {"bound": "hbm", "kernel": "gemm_kernel<1> (tcgen05 projection GEMM: all launches of one step, per GPU)",
@@ -306,7 +317,7 @@ def main():
     if world == 1 and args.cpu_steps > 0:
         w = O.parse_st(st)
         ctoks = toks[:, PROMPT:PROMPT + args.cpu_steps + 1]
-        tps, cms, threads = cpu_arm(w, BATCH, args.cpu_steps, 1, ctoks)
+        tps, cms, threads, _ = cpu_arm(w, BATCH, args.cpu_steps, 1, ctoks, budget_s=30.0)
         cpu = {"value": tps, "unit": "tokens/s", "cores": threads, "kind": "port", "ms_per_step": cms,
                "sample": f"{args.cpu_steps} decode steps of the same workload on the host cores (C/OpenMP oracle, "
                          "f16 weights, f32 math); reference web-rwkv/lavapipe path unbuildable here"}

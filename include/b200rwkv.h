@@ -66,8 +66,11 @@ int32_t b200rwkv_info_from_st(const uint8_t* st, size_t len, b200rwkv_info* out)
 /* Replaces `ModelBuilder::new(ctx, st).build_vN()` + `vN::Bundle::<f16>::new(model, max_batch)`
  * + `TokioRuntime::<Rnn>::new(bundle)` — crates/ai00-core/src/lib.rs:484-515.
  * `device` is the CUDA ordinal (the reference's adapter selection, lib.rs:351-368).
- * precision: 0 = fp16 weights (f32 accumulate/state/logits); 1 (fp32) is rejected with
- * B200RWKV_ERR_UNSUPPORTED. */
+ * precision (the reference's `Precision`, lib.rs:493: `Bundle::<f16>` / `Bundle::<f32>` = the ACTIVATION type; weights
+ * are f16 on disk and in HBM either way):
+ *   0 = fp16: every projection input is rounded to f16 (tensor-core operand), f32 accumulate / state / logits;
+ *   1 = fp32: no activation is rounded -- every projection input travels as an f16 hi + lo pair (two operand tiles,
+ *       accumulators added), which is f32-exact to ~2^-22; steps are capped at 16 tokens; single GPU. */
 int32_t b200rwkv_create(const uint8_t* st, size_t len, int32_t device, int32_t max_batch,
                         int32_t token_chunk_size, int32_t precision, b200rwkv_engine** out);
 

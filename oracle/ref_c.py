@@ -34,6 +34,8 @@ def _lib():
     lib.ref_decode_step.argtypes = [C.POINTER(RefModel), C.c_int32, _P, _P, _P]
     lib.ref_decode_step.restype = C.c_int32
     lib.ref_num_threads.restype = C.c_int32
+    lib.ref_set_num_threads.argtypes = [C.c_int32]
+    lib.ref_set_num_threads.restype = None
     return lib
 
 
@@ -94,6 +96,9 @@ class RefC:
 
     def num_threads(self) -> int:
         return int(self.lib.ref_num_threads())
+
+    def set_num_threads(self, n: int) -> None:
+        self.lib.ref_set_num_threads(int(n))
 
     def state_init(self, B: int) -> np.ndarray:
         i = self.info

@@ -396,6 +396,15 @@ int ref_decode_step(const RefModel* m, int B, const int32_t* tokens, float* stat
     return 0;
 }
 
+/* The benchmark's CPU arms size the team themselves: under torchrun the environment carries OMP_NUM_THREADS=1. */
+void ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int ref_num_threads(void) {
     int n = 1;
 #ifdef _OPENMP

@@ -58,12 +58,57 @@ def test_create_fails_loudly_without_gpu():
     assert "no CPU fallback" in str(ei.value)
 
 
-def test_fp32_precision_rejected():
+def test_bad_precision_rejected():
+    """precision 0 = f16 activations, 1 = f32-exact activations (web-rwkv Bundle::<f32>); anything else is invalid."""
     st = synth.make_st("tiny6", 0)
     h = C.c_void_p()
-    code = capi.lib().b200rwkv_create(capi.ptr(st), st.size, 0, 2, 16, 1, C.byref(h))
-    assert code == capi.ERR_UNSUPPORTED
+    code = capi.lib().b200rwkv_create(capi.ptr(st), st.size, 0, 2, 16, 7, C.byref(h))
+    assert code == capi.ERR_INVALID
     assert not h.value
+
+
+def _edit_header(st: np.ndarray, fn) -> np.ndarray:
+    import json
+    import struct
+    raw = st.tobytes()
+    hlen = struct.unpack("<Q", raw[:8])[0]
+    hdr = json.loads(raw[8:8 + hlen])
+    fn(hdr)
+    h2 = json.dumps(hdr, separators=(",", ":")).encode()
+    return np.frombuffer(struct.pack("<Q", len(h2)) + h2 + raw[8 + hlen:], dtype=np.uint8).copy()
+
+
+def test_st_tensor_sizes_are_validated():
+    """A tensor whose byte range does not equal dtype x shape, a wrong rank, or an absurd shape must be a clean
+    B200RWKV_ERR_INVALID from the host-only parser (the loader trusted shape-derived sizes)."""
+    st = synth.make_st("tiny6", 0)
+    assert capi.info_from_st(st)["version"] == 6
+
+    def short_tensor(h):
+        b, e = h["blocks.0.att.key.weight"]["data_offsets"]
+        h["blocks.0.att.key.weight"]["data_offsets"] = [b, e - 64]
+
+    def huge_shape(h):
+        h["emb.weight"]["shape"] = [1 << 40, 1 << 40]
+
+    def wrong_rank(h):
+        t = h["blocks.0.att.time_first"]
+        t["shape"] = [int(np.prod(t["shape"]))]
+
+    def bad_dtype(h):
+        h["emb.weight"]["dtype"] = "Q7"
+
+    def deep_metadata(h):
+        node = cur = {}
+        for _ in range(200):
+            cur["x"] = {}
+            cur = cur["x"]
+        h["__metadata__"] = node
+
+    for fn in (short_tensor, huge_shape, wrong_rank, bad_dtype, deep_metadata):
+        with pytest.raises(capi.B200Error) as ei:
+            capi.info_from_st(_edit_header(st, fn))
+        assert ei.value.code == capi.ERR_INVALID, fn.__name__
 
 
 def test_runtime_chunking_bookkeeping():
