@@ -20,6 +20,7 @@
 #include "gemm.cuh"
 #include "lora.cuh"
 #include "pre6.cuh"
+#include "sample.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
 #include "mix.cuh"
@@ -398,8 +399,21 @@ struct b200rwkv_engine {
     float *sm_in = nullptr, *sm_out = nullptr;
     int sm_rows_cap = 0;
 
+    // sampling front half (sample.cuh): last logits row of every slot, candidate scratch, staging blobs
+    float* d_keep = nullptr;                 // [S][V] (rank 0)
+    std::vector<char> keep_valid;            // slot has a logits row (guarded by keep_mu)
+    std::mutex keep_mu;
+    cudaEvent_t step_done = nullptr;         // recorded on `stream` after every step: the sampling stream waits on it
+    float* tk_cand_x = nullptr; unsigned* tk_cand_id = nullptr; float2* tk_stats = nullptr;
+    unsigned* tk_out_id = nullptr; float* tk_out_p = nullptr;
+    uint8_t *tk_dev = nullptr, *tk_host = nullptr;
+    size_t tk_cap = 0;
+    void enqueue_keep(cudaStream_t s, int MTR);
+    void sample_topk(int nrows, const int32_t* slots, const int32_t* pen_off, const uint32_t* pen_tok, const float* pen_val,
+                     const uint32_t* allow_bits, const int32_t* bias_off, const uint32_t* bias_tok, const float* bias_val,
+                     int top_k, uint32_t* ids_out, float* probs_out);
+
     std::mutex mu, sm_mu;
-    std::string err;
 
     // temp upload buffer during build
     __half* d_tmp = nullptr;
@@ -472,6 +486,9 @@ b200rwkv_engine::~b200rwkv_engine() {
     if (sm_in) cudaFree(sm_in);
     if (sm_out) cudaFree(sm_out);
     if (h_meta) cudaFreeHost(h_meta);
+    if (tk_dev) cudaFree(tk_dev);
+    if (tk_host) cudaFreeHost(tk_host);
+    if (step_done) cudaEventDestroy(step_done);
     if (stream) cudaStreamDestroy(stream);
     if (sm_stream) cudaStreamDestroy(sm_stream);
 }
@@ -762,6 +779,19 @@ void b200rwkv_engine::build(const StFile& st) {
     const int S_att = pick_split(Cl, cdiv(C, GEMM_BN)), S_ffn = pick_split(Fl, cdiv(C, GEMM_BN));
     split_att = S_att; split_ffn = S_ffn;
     d_hidden = (float*)dalloc(TC * 4);
+    CK(cudaEventCreateWithFlags(&step_done, cudaEventDisableTiming));
+    keep_valid.assign(S, 0);
+    if (rank == 0) {
+        d_keep = (float*)dalloc((size_t)S * V * 4);
+        const int nseg = cdiv(V, TOPK_SEG);
+        if (nseg <= TOPK_MAX_SEGS) {       // larger vocabularies: b200rwkv_sample_topk answers UNSUPPORTED
+            tk_cand_x = (float*)dalloc((size_t)S * nseg * TOPK_MAX * 4);
+            tk_cand_id = (unsigned*)dalloc((size_t)S * nseg * TOPK_MAX * 4);
+            tk_stats = (float2*)dalloc((size_t)S * nseg * 8);
+            tk_out_id = (unsigned*)dalloc((size_t)S * TOPK_MAX * 4);
+            tk_out_p = (float*)dalloc((size_t)S * TOPK_MAX * 4);
+        }
+    }
     for (int i = 0; i < 6; ++i) a_x[i] = a16_alloc(C);
     a_out = a16_alloc(Cl);
     a_kk = a16_alloc(Fl);
@@ -1423,11 +1453,24 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
 
 static inline int mt_bucket(int rows) { return rows <= 16 ? 1 : (rows <= 32 ? 2 : 4); }
 
+// last logits row of every slot of this step -> keep[slot] (rank 0 gathers the vocabulary shards); see sample.cuh
+void b200rwkv_engine::enqueue_keep(cudaStream_t s, int MTR) {
+    if (MTR <= 0 || rank != 0 || !d_keep || Vl % 4 != 0) return;
+    KeepParams kp;
+    memset(&kp, 0, sizeof(kp));
+    for (int q = 0; q < world; ++q) kp.shard[q] = (const float*)(peer_base[q] + off_logits);
+    kp.world = world; kp.Vl = Vl; kp.V = V;
+    kp.meta = MetaView{d_meta, maxT, S};
+    kp.keep = d_keep;
+    launch_k(keep_rows_kernel, dim3(MTR * 16, KEEP_CHUNKS), dim3(KEEP_THREADS), 0, kp, KC_OTHER, s, nullptr);
+}
+
 void b200rwkv_engine::run_step(int MT, int MTR) {
     const bool mega_step = mega_ok && MT == 1 && MTR <= 1;
     if (!use_graph) {
         if (mega_step) launch_mega(stream);
         else enqueue_step(stream, MT, MTR, nullptr);
+        enqueue_keep(stream, MTR);
         return;
     }
     const int key = mega_step ? 0 : MT * 8 + MTR;
@@ -1438,6 +1481,7 @@ void b200rwkv_engine::run_step(int MT, int MTR) {
         try {
             if (mega_step) launch_mega(stream);
             else enqueue_step(stream, MT, MTR, nullptr);
+            enqueue_keep(stream, MTR);
         } catch (...) {
             cudaStreamEndCapture(stream, &g);
             if (g) cudaGraphDestroy(g);
@@ -1528,8 +1572,9 @@ void b200rwkv_engine::infer(int nslot, const int32_t* slot, const int32_t* ntok,
     for (size_t i = 0; i < total_tok; ++i)
         REQUIRE(tokens[i] < (uint32_t)V, B200RWKV_ERR_INVALID, "infer: token id " + std::to_string(tokens[i]) + " is outside the vocabulary");
     const bool want_logits = (rank == 0);          // tensor parallel: rank 0 gathers all vocabulary shards
-    REQUIRE(!want_logits || total_rows * (size_t)V <= cap || total_rows == 0, B200RWKV_ERR_INVALID, "infer: logits buffer too small");
-    REQUIRE(!want_logits || total_rows == 0 || logits_out, B200RWKV_ERR_INVALID, "infer: null logits buffer");
+    REQUIRE(!want_logits || !logits_out || total_rows * (size_t)V <= cap || total_rows == 0, B200RWKV_ERR_INVALID, "infer: logits buffer too small");
+    // logits_out == NULL: the rows stay in HBM (b200rwkv_sample_topk reads the last row of every slot from there)
+    const bool copy_logits = want_logits && logits_out != nullptr;
     // f32-activation mode runs every step decode-shaped (<= 16 tokens): the split-operand kernels are the 16-token ones
     const int step_cap = std::min(chunk, split_on ? 16 : maxT);
     // cursor over entries
@@ -1561,7 +1606,13 @@ void b200rwkv_engine::infer(int nslot, const int32_t* slot, const int32_t* ntok,
         last_T = T;
         CK(cudaMemcpyAsync(d_meta, h_meta, meta_ints * 4, cudaMemcpyHostToDevice, stream));
         run_step(mt_bucket(T), R > 0 ? mt_bucket(R) : 0);
-        if (R > 0 && want_logits) {
+        CK(cudaEventRecord(step_done, stream));
+        if (R > 0) {
+            std::lock_guard<std::mutex> lk(keep_mu);
+            for (size_t i = 0; i < s_slots.size(); ++i)
+                if (s_out[i] != 0) keep_valid[s_slots[i]] = 1;
+        }
+        if (R > 0 && copy_logits) {
             if (world == 1) {
                 CK(cudaMemcpyAsync(out, d_logits, (size_t)R * V * 4, cudaMemcpyDeviceToHost, stream));
             } else {
@@ -1573,6 +1624,76 @@ void b200rwkv_engine::infer(int nslot, const int32_t* slot, const int32_t* ntok,
         }
         CK(cudaStreamSynchronize(stream));
     }
+}
+
+// GPU sampling front half (sample.cuh).  Runs on the softmax stream under the softmax mutex: the reference samples from the
+// task that owns softmax (run.rs:1237), concurrently with the infer task; the per-slot rows it reads are only rewritten by a
+// step that contains the slot, which the host cannot submit before this call returned the slot's token.
+void b200rwkv_engine::sample_topk(int nrows, const int32_t* slots, const int32_t* pen_off, const uint32_t* pen_tok, const float* pen_val,
+                                  const uint32_t* allow_bits, const int32_t* bias_off, const uint32_t* bias_tok, const float* bias_val,
+                                  int top_k, uint32_t* ids_out, float* probs_out) {
+    REQUIRE(rank == 0, B200RWKV_ERR_INVALID, "sample_topk: only rank 0 holds the gathered logits");
+    REQUIRE(tk_cand_x, B200RWKV_ERR_UNSUPPORTED, "sample_topk: num_vocab > 65536 is not supported");
+    REQUIRE(nrows >= 1 && nrows <= S && slots && ids_out && probs_out, B200RWKV_ERR_INVALID, "sample_topk: bad argument");
+    REQUIRE(top_k >= 1 && top_k <= TOPK_MAX, B200RWKV_ERR_INVALID, "sample_topk: top_k must be in [1, 128]");
+    {
+        std::lock_guard<std::mutex> lk(keep_mu);
+        std::vector<char> seen(S, 0);
+        for (int i = 0; i < nrows; ++i) {
+            REQUIRE(slots[i] >= 0 && slots[i] < S, B200RWKV_ERR_STATE, "sample_topk: slot out of range");
+            REQUIRE(!seen[slots[i]], B200RWKV_ERR_INVALID, "sample_topk: duplicate slot");
+            seen[slots[i]] = 1;
+            REQUIRE(keep_valid[slots[i]], B200RWKV_ERR_STATE, "sample_topk: slot " + std::to_string(slots[i]) + " has produced no logits row yet");
+        }
+    }
+    const int npen = pen_off ? pen_off[nrows] : 0, nbias = bias_off ? bias_off[nrows] : 0;
+    REQUIRE(npen >= 0 && nbias >= 0 && (npen == 0 || (pen_tok && pen_val)) && (nbias == 0 || (bias_tok && bias_val)), B200RWKV_ERR_INVALID,
+            "sample_topk: bad adjustment lists");
+    for (int i = 0; i < nrows; ++i) {
+        REQUIRE(!pen_off || (pen_off[i] >= 0 && pen_off[i] <= pen_off[i + 1]), B200RWKV_ERR_INVALID, "sample_topk: penalty offsets must ascend");
+        REQUIRE(!bias_off || (bias_off[i] >= 0 && bias_off[i] <= bias_off[i + 1]), B200RWKV_ERR_INVALID, "sample_topk: bias offsets must ascend");
+    }
+    const size_t words = (size_t)(V + 31) / 32;
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    // one staging blob: slot[n] | pen_off[n+1] | bias_off[n+1] | pen_tok | pen_val | bias_tok | bias_val | allow
+    const size_t o_slot = 0, o_po = al(o_slot + (size_t)nrows * 4), o_bo = al(o_po + (size_t)(nrows + 1) * 4),
+                 o_pt = al(o_bo + (size_t)(nrows + 1) * 4), o_pv = al(o_pt + (size_t)npen * 4), o_bt = al(o_pv + (size_t)npen * 4),
+                 o_bv = al(o_bt + (size_t)nbias * 4), o_al = al(o_bv + (size_t)nbias * 4),
+                 total = al(o_al + (allow_bits ? (size_t)nrows * words * 4 : 0));
+    if (total > tk_cap) {
+        if (tk_dev) { CK(cudaFree(tk_dev)); tk_dev = nullptr; }
+        if (tk_host) { CK(cudaFreeHost(tk_host)); tk_host = nullptr; }
+        tk_cap = 0;
+        const size_t want = std::max<size_t>(total * 2, 1 << 20);
+        CK(cudaMalloc(&tk_dev, want));
+        CK(cudaMallocHost(&tk_host, want));
+        tk_cap = want;
+    }
+    std::vector<int32_t> zeros(nrows + 1, 0);
+    memcpy(tk_host + o_slot, slots, (size_t)nrows * 4);
+    memcpy(tk_host + o_po, pen_off ? pen_off : zeros.data(), (size_t)(nrows + 1) * 4);
+    memcpy(tk_host + o_bo, bias_off ? bias_off : zeros.data(), (size_t)(nrows + 1) * 4);
+    if (npen) { memcpy(tk_host + o_pt, pen_tok, (size_t)npen * 4); memcpy(tk_host + o_pv, pen_val, (size_t)npen * 4); }
+    if (nbias) { memcpy(tk_host + o_bt, bias_tok, (size_t)nbias * 4); memcpy(tk_host + o_bv, bias_val, (size_t)nbias * 4); }
+    if (allow_bits) memcpy(tk_host + o_al, allow_bits, (size_t)nrows * words * 4);
+    CK(cudaStreamWaitEvent(sm_stream, step_done, 0));
+    CK(cudaMemcpyAsync(tk_dev, tk_host, total, cudaMemcpyHostToDevice, sm_stream));
+    TopkParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.keep = d_keep; tp.V = V; tp.nseg = cdiv(V, TOPK_SEG);
+    tp.slot = (const int*)(tk_dev + o_slot);
+    tp.pen_off = (const int*)(tk_dev + o_po); tp.pen_tok = (const unsigned*)(tk_dev + o_pt); tp.pen_val = (const float*)(tk_dev + o_pv);
+    tp.bias_off = (const int*)(tk_dev + o_bo); tp.bias_tok = (const unsigned*)(tk_dev + o_bt); tp.bias_val = (const float*)(tk_dev + o_bv);
+    tp.allow = allow_bits ? (const unsigned*)(tk_dev + o_al) : nullptr;
+    tp.cand_x = tk_cand_x; tp.cand_id = tk_cand_id; tp.stats = tk_stats;
+    tp.top_k = top_k; tp.out_id = tk_out_id; tp.out_p = tk_out_p;
+    topk_segment_kernel<<<dim3(tp.nseg, nrows), TOPK_SEG_THREADS, 0, sm_stream>>>(tp);
+    CK(cudaGetLastError());
+    topk_merge_kernel<<<nrows, TOPK_MERGE_THREADS, 0, sm_stream>>>(tp);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ids_out, tk_out_id, (size_t)nrows * top_k * 4, cudaMemcpyDeviceToHost, sm_stream));
+    CK(cudaMemcpyAsync(probs_out, tk_out_p, (size_t)nrows * top_k * 4, cudaMemcpyDeviceToHost, sm_stream));
+    CK(cudaStreamSynchronize(sm_stream));
 }
 
 void b200rwkv_engine::state_xform(int slot, bool import) {
@@ -1589,19 +1710,24 @@ void b200rwkv_engine::state_xform(int slot, bool import) {
 // =========================================================================================
 // C ABI
 // =========================================================================================
+// Error text is thread-local: the reference makes engine calls from two tasks (infer / softmax, run.rs:1232-1237) and a
+// per-engine string would race between them.  b200rwkv_last_error() returns the message of the calling thread's last failure.
 #define API_BEGIN(e)                            \
-    std::string* errp_ = (e) ? &(e)->err : &g_err; \
+    std::string* errp_ = &g_err;                \
+    (void)(e);                                  \
     try {
 #define API_END                                  \
     }                                            \
     catch (const Error& ex) {                    \
         *errp_ = ex.what();                      \
-        g_err = ex.what();                       \
         return ex.code;                          \
     }                                            \
     catch (const std::exception& ex) {           \
         *errp_ = ex.what();                      \
-        g_err = ex.what();                       \
+        return B200RWKV_ERR_INVALID;             \
+    }                                            \
+    catch (...) {                                \
+        *errp_ = "unknown exception";            \
         return B200RWKV_ERR_INVALID;             \
     }                                            \
     return B200RWKV_OK;
@@ -1872,6 +1998,19 @@ int32_t b200rwkv_softmax(b200rwkv_engine* e, int32_t rows, const float* in, floa
     API_END
 }
 
+int32_t b200rwkv_sample_topk(b200rwkv_engine* e, int32_t nrows, const int32_t* slots, const int32_t* penalty_offset,
+                             const uint32_t* penalty_token, const float* penalty_value, const uint32_t* allow_bits,
+                             const int32_t* bias_offset, const uint32_t* bias_token, const float* bias_value, int32_t top_k,
+                             uint32_t* ids_out, float* probs_out) {
+    API_BEGIN(e)
+    REQUIRE(e, B200RWKV_ERR_INVALID, "null engine");
+    std::lock_guard<std::mutex> lk(e->sm_mu);
+    CK(cudaSetDevice(e->dev));
+    e->sample_topk(nrows, slots, penalty_offset, penalty_token, penalty_value, allow_bits, bias_offset, bias_token, bias_value, top_k,
+                   ids_out, probs_out);
+    API_END
+}
+
 int32_t b200rwkv_host_alloc(size_t bytes, void** out) {
     API_BEGIN((b200rwkv_engine*)nullptr)
     REQUIRE(out, B200RWKV_ERR_INVALID, "null out");
@@ -1968,7 +2107,7 @@ int32_t b200rwkv_profile_step(b200rwkv_engine* e, int32_t nslot, const int32_t* 
 
 int32_t b200rwkv_last_hidden(b200rwkv_engine* e, float* out, size_t cap) {
     if (!e || !out) return B200RWKV_ERR_INVALID;
-    std::string* errp_ = &e->err;
+    std::string* errp_ = &g_err;
     try {
         std::lock_guard<std::mutex> lk(e->mu);
         CK(cudaSetDevice(e->dev));
@@ -1987,7 +2126,7 @@ int32_t b200rwkv_last_hidden(b200rwkv_engine* e, float* out, size_t cap) {
 // capped by `cap`), or a negative status.  Not used on the product path.
 int32_t b200rwkv_debug_read(b200rwkv_engine* e, const char* name, float* out, size_t cap) {
     if (!e || !name || !out) return B200RWKV_ERR_INVALID;
-    std::string* errp_ = &e->err;
+    std::string* errp_ = &g_err;
     try {
         std::lock_guard<std::mutex> lk(e->mu);
         CK(cudaSetDevice(e->dev));
@@ -2051,7 +2190,7 @@ int32_t b200rwkv_debug_trace(b200rwkv_engine* e, uint64_t* out, size_t cap, int3
         *nphase = (int32_t)nl;
         return B200RWKV_OK;
     }
-    if (!e->mega_ok || !e->mega.trace) { e->err = "no trace (set B200RWKV_TRACE=1)"; return B200RWKV_ERR_INVALID; }
+    if (!e->mega_ok || !e->mega.trace) { g_err = "no trace (set B200RWKV_TRACE=1)"; return B200RWKV_ERR_INVALID; }
     const size_t n = (size_t)4 * e->mega.nphase * 12;
     if (cap < n) return B200RWKV_ERR_INVALID;
     cudaSetDevice(e->dev);
@@ -2149,6 +2288,6 @@ int32_t b200rwkv_debug_stream(int32_t device, int32_t kind, double gbytes, int32
     API_END
 }
 
-const char* b200rwkv_last_error(b200rwkv_engine* e) { return e ? e->err.c_str() : g_err.c_str(); }
+const char* b200rwkv_last_error(b200rwkv_engine* e) { (void)e; return g_err.c_str(); }
 
 }  // extern "C"

@@ -114,6 +114,47 @@ class State:
         capi.check(capi.lib().b200rwkv_state_write(self._m._h, batch, tensor.id), self._m._h)
 
 
+class NucleusSampler:
+    """Host back half of the reference's `NucleusSampler` (sampler/nucleus.rs:13-123) over the <= 128 candidates the GPU
+    front half returns: same parameters, same penalty state, same arithmetic in f32; `rand` is the uniform draw the
+    reference takes from fastrand (nucleus.rs:104), passed in so tests are deterministic."""
+
+    def __init__(self, top_p=0.5, top_k=128, temperature=1.0, presence_penalty=0.3, frequency_penalty=0.3,
+                 penalty_decay=0.99654026):
+        f = np.float32
+        self.top_p, self.top_k, self.temperature = f(top_p), int(top_k), f(temperature)
+        self.presence_penalty, self.frequency_penalty, self.penalty_decay = f(presence_penalty), f(frequency_penalty), f(penalty_decay)
+        self.penalties: dict[int, np.float32] = {}
+
+    def init(self, model_tokens):                                   # nucleus.rs:50-59
+        for index, token in enumerate(reversed(list(model_tokens))):
+            pen = self.penalties.pop(int(token), self.presence_penalty)
+            pen = np.float32(pen + self.frequency_penalty * np.float32(np.power(self.penalty_decay, np.float32(index))))
+            self.penalties[int(token)] = pen
+
+    def sample_candidates(self, ids, probs, rand: float) -> int:   # nucleus.rs:69-123 after the sort / take(top_k)
+        f = np.float32
+        kept, cum = [], f(0.0)
+        for i, x in zip(ids[:self.top_k], probs[:self.top_k]):
+            if cum > self.top_p:
+                break
+            cum = f(cum + x)
+            kept.append((int(i), f(np.power(f(x), f(1.0) / self.temperature))))
+        total = f(0.0)
+        for _, x in kept:
+            total = f(total + x)
+        token, cum = kept[0][0], f(0.0)
+        for i, x in kept:
+            cum = f(cum + f(x / total))
+            if f(rand) <= cum:
+                token = i
+                break
+        for t in self.penalties:
+            self.penalties[t] = f(self.penalties[t] * self.penalty_decay)
+        self.penalties[token] = f(self.penalties[token] + self.frequency_penalty) if token in self.penalties else self.presence_penalty
+        return token
+
+
 class Runtime:
     """`Arc<dyn Runtime<Rnn>>`.  `infer` consumes at most `token_chunk_size` tokens of the
     input across slots and returns the remaining input with the per-slot outputs, exactly the
@@ -183,11 +224,18 @@ class Model:
             pass
 
     # ---- raw call: one b200rwkv_infer ----
-    def infer_raw(self, slots, ntok, tokens, options, out: np.ndarray | None = None):
+    def infer_raw(self, slots, ntok, tokens, options, out: np.ndarray | None = None, keep_on_device: bool = False):
         V = self.info["num_vocab"]          # rank 0 receives the gathered full-vocabulary rows
         n = len(slots)
         total = sum(nt if o == capi.OPTION_FULL else (1 if (o == capi.OPTION_LAST and nt > 0) else 0)
                     for nt, o in zip(ntok, options))
+        if keep_on_device:                  # logits_out = NULL: rows stay in HBM for sample_topk
+            a_slot, a_ntok = np.asarray(slots, np.int32), np.asarray(ntok, np.int32)
+            a_tok, a_opt = np.asarray(tokens, np.uint32), np.asarray(options, np.int32)
+            a_rows = np.zeros(max(n, 1), np.int32)
+            capi.check(capi.lib().b200rwkv_infer(self._h, n, capi.ptr(a_slot), capi.ptr(a_ntok), capi.ptr(a_tok),
+                                                 capi.ptr(a_opt), None, 0, capi.ptr(a_rows)), self._h)
+            return [int(r) for r in a_rows[:n]]
         if out is None:
             out = np.empty((max(total, 1), V), np.float32)
         a_slot = np.asarray(slots, np.int32)
@@ -212,6 +260,41 @@ class Model:
         y = np.empty_like(x)
         capi.check(capi.lib().b200rwkv_softmax(self._h, x.shape[0], capi.ptr(x), capi.ptr(y)), self._h)
         return [y[i] for i in range(y.shape[0])]
+
+    def sample_topk(self, slots, penalties=None, bias=None, allow=None, top_k: int = 128):
+        """GPU front half of sampling (b200rwkv_sample_topk): for each slot the `top_k` most probable tokens of its last
+        logits row after penalties / grammar mask / bias, as (ids [n, top_k] uint32, probs [n, top_k] f32).
+        penalties, bias: per-slot dict token -> value (the reference's HashMaps, nucleus.rs:29, run.rs:679);
+        allow: optional [n, V] bool array (tokens the formatter allows)."""
+        n = len(slots)
+        V = self.info["num_vocab"]
+
+        def pack(maps):
+            off = np.zeros(n + 1, np.int32)
+            toks, vals = [], []
+            for i in range(n):
+                m = (maps[i] if maps is not None else None) or {}
+                toks.extend(int(t) for t in m.keys())
+                vals.extend(float(v) for v in m.values())
+                off[i + 1] = len(toks)
+            return off, np.asarray(toks, np.uint32), np.asarray(vals, np.float32)
+
+        po, pt, pv = pack(penalties)
+        bo, bt, bv = pack(bias)
+        bits = None
+        if allow is not None:
+            a = np.asarray(allow, bool).reshape(n, V)
+            words = (V + 31) // 32
+            padded = np.zeros((n, words * 32), bool)
+            padded[:, :V] = a
+            bits = np.ascontiguousarray(np.packbits(padded.reshape(n, words, 32), axis=2, bitorder="little").view(np.uint32).reshape(n, words))
+        ids = np.empty((n, top_k), np.uint32)
+        probs = np.empty((n, top_k), np.float32)
+        a_slot = np.asarray(slots, np.int32)
+        capi.check(capi.lib().b200rwkv_sample_topk(self._h, n, capi.ptr(a_slot), capi.ptr(po), capi.ptr(pt), capi.ptr(pv),
+                                                   capi.ptr(bits) if bits is not None else None, capi.ptr(bo), capi.ptr(bt),
+                                                   capi.ptr(bv), top_k, capi.ptr(ids), capi.ptr(probs)), self._h)
+        return ids, probs
 
     def last_hidden(self) -> np.ndarray:
         Cc = self.info["num_emb"]

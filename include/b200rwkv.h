@@ -7,8 +7,9 @@
  *
  * Conventions
  *   - every function returns 0 on success, a negative b200rwkv_status on failure; the message
- *     is available from b200rwkv_last_error() (per engine, or thread-global when the engine
- *     pointer is NULL / creation failed).  No exception crosses the boundary.
+ *     of the calling thread's most recent failure is available from b200rwkv_last_error()
+ *     (thread-local: the infer task and the softmax task never see each other's text).  No
+ *     exception crosses the boundary.
  *   - all buffers are caller-owned plain host memory unless stated; nothing is retained after
  *     the call returns (the `.st` image is only borrowed during b200rwkv_create).
  *   - threading mirrors the reference: ONE task calls infer/state ops
@@ -103,7 +104,9 @@ int32_t b200rwkv_get_info(b200rwkv_engine*, b200rwkv_info* out);
  * web-rwkv applies across calls at run.rs:1134-1145).  Logits rows (num_vocab f32 each) are
  * written contiguously to `logits_out` in entry order: 1 row for LAST (0 if ntok[i]==0),
  * ntok[i] rows for FULL, none for NONE; rows_out[i] receives the row count of entry i
- * (== RnnOutputBatch being empty or not, run.rs:1146-1155).  `logits_cap` is in floats. */
+ * (== RnnOutputBatch being empty or not, run.rs:1146-1155).  `logits_cap` is in floats.
+ * `logits_out` may be NULL: nothing is copied to the host, the last row of every slot stays in HBM for
+ * b200rwkv_sample_topk.  Token ids >= num_vocab are B200RWKV_ERR_INVALID. */
 int32_t b200rwkv_infer(b200rwkv_engine*, int32_t nslot, const int32_t* slot, const int32_t* ntok,
                        const uint32_t* tokens, const int32_t* option, float* logits_out,
                        size_t logits_cap, int32_t* rows_out);
@@ -122,6 +125,26 @@ int32_t b200rwkv_state_free(b200rwkv_engine*, uint64_t snapshot_id);            
 /* Replaces `web_rwkv::runtime::softmax::softmax(&context, Vec<TensorCpu<f32>>)` —
  * crates/ai00-core/src/run.rs:1179.  in/out: [rows, num_vocab] f32. */
 int32_t b200rwkv_softmax(b200rwkv_engine*, int32_t rows, const float* in, float* out);
+
+/* GPU front half of token sampling.  Replaces, for samplers that only need the head of the sorted
+ * distribution (Nucleus with top_k <= 128 -- the reference default, sampler/nucleus.rs:16-17 -- and greedy), the per-token
+ * per-slot sequence of crates/ai00-core/src/run.rs:664-697: `output.to_vec()` (num_vocab f32 D2H), `Sampler::transform`
+ * (penalties, sampler/nucleus.rs:61-67), `Formatter::transform` (BNF mask, sampler/bnf.rs:37-40), the bias add
+ * (run.rs:679-681), the softmax round trip (run.rs:1164-1190) and the full-vocabulary sort of
+ * sampler/nucleus.rs:69-80.  Pass `logits_out = NULL` to b200rwkv_infer: the logits stay in HBM, and this call returns, for
+ * each listed slot, the `top_k` most probable tokens of that slot's most recent logits row after
+ *     logits[penalty_token[j]] -= penalty_value[j]     j in [penalty_offset[i], penalty_offset[i+1])
+ *     logits[t] = -inf  where bit t of allow_bits row i is 0                    (allow_bits may be NULL)
+ *     logits[bias_token[j]]    += bias_value[j]        j in [bias_offset[i], bias_offset[i+1])
+ * (tokens distinct within one row's penalty list and within its bias list, as the reference's HashMaps are), with
+ * probs = softmax over the whole adjusted row.  Order: logit descending, token id ascending on ties.  ids_out / probs_out:
+ * [nrows][top_k].  The draw itself (top_p cut, temperature, RNG, penalty update; nucleus.rs:81-123) stays in the host
+ * sampler, now over <= 128 pairs.  Samplers that need the whole distribution (Mirostat, Typical) keep using
+ * b200rwkv_infer with a logits buffer + b200rwkv_softmax.  Thread contract: the softmax task's (run.rs:1237). */
+int32_t b200rwkv_sample_topk(b200rwkv_engine*, int32_t nrows, const int32_t* slots, const int32_t* penalty_offset,
+                             const uint32_t* penalty_token, const float* penalty_value, const uint32_t* allow_bits,
+                             const int32_t* bias_offset, const uint32_t* bias_token, const float* bias_value, int32_t top_k,
+                             uint32_t* ids_out, float* probs_out);
 
 /* Pinned host memory for logits / state buffers (full-rate DMA); optional. */
 int32_t b200rwkv_host_alloc(size_t bytes, void** out);
