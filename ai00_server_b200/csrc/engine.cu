@@ -460,8 +460,10 @@ struct b200rwkv_engine {
     std::vector<int> step_trace_types;
     static constexpr int STEP_TRACE_MAX = 1024;
     static constexpr int STEP_TRACE_ROW = 512;     // 8 stamps of CTA 0 + {SM id, last MMA, exit} of every projection CTA
+    bool trace_capture = false;                    // stamps are wired into the launches being enqueued / captured right now
+    std::vector<long long> step_trace_bytes;       // algorithmic weight bytes of each traced projection launch
     unsigned long long* tr_next(int label) {
-        if (!d_step_trace || launches_last_step >= STEP_TRACE_MAX) return nullptr;
+        if (!d_step_trace || !trace_capture || launches_last_step >= STEP_TRACE_MAX) return nullptr;
         if ((int)step_trace_types.size() <= launches_last_step) step_trace_types.resize(launches_last_step + 1);
         step_trace_types[launches_last_step] = label;
         return d_step_trace + (size_t)STEP_TRACE_ROW * launches_last_step;
@@ -771,7 +773,10 @@ void b200rwkv_engine::build(const StFile& st) {
         d_logits = (float*)(comm_base + off_logits);
         d_epoch = (unsigned*)dalloc(16, true);
         pre_gbar = (unsigned*)dalloc(256, true);
-        if (getenv("B200RWKV_STEP_TRACE")) d_step_trace = (unsigned long long*)dalloc((size_t)STEP_TRACE_MAX * STEP_TRACE_ROW * 8, true);
+        if (getenv("B200RWKV_STEP_TRACE")) {
+            d_step_trace = (unsigned long long*)dalloc((size_t)STEP_TRACE_MAX * STEP_TRACE_ROW * 8, true);
+            trace_capture = true;
+        }
         ln_cluster_ok = ln_cluster && C % (4 * PRE_CLUSTER) == 0 && C / (4 * PRE_CLUSTER) <= PRE_THREADS;
         split_on = split_act && ln_cluster_ok && !use_mega && !lora_cc;
         REQUIRE(precision != 1 || split_on, B200RWKV_ERR_UNSUPPORTED, "precision 1 needs num_emb to be a multiple of 32 and <= 8192");
@@ -1331,7 +1336,11 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
     size_t seq_pos = 0;
     auto launch_gemm_chained = [&](const GemmLaunch& g, int mt) {
         GemmLaunch g2 = g;
-        if (d_step_trace) g2.p.trace = tr_next(1000000 + (int)(g.weight_bytes >> 20));
+        if (d_step_trace && trace_capture) {
+            g2.p.trace = tr_next(1000000 + (int)(g.weight_bytes >> 20));
+            if ((long long)step_trace_bytes.size() <= launches_last_step) step_trace_bytes.resize(launches_last_step + 1, 0);
+            step_trace_bytes[launches_last_step] = (long long)g.weight_bytes;
+        }
         if (!seq.empty()) {
             REQUIRE(seq_pos < seq.size() && seq[seq_pos] == &g, B200RWKV_ERR_INVALID, "internal: projection launch order");
             const GemmLaunch& nx = *seq[(seq_pos + 1) % seq.size()];
@@ -2037,7 +2046,7 @@ static void build_decode_metas(b200rwkv_engine* e, int nslot, const int32_t* slo
 }
 
 int32_t b200rwkv_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, int32_t warmup,
-                              int32_t steps, int32_t flush_l2, float* ms_out, int64_t* launches_out) {
+                              int32_t steps, int32_t flush_l2, float* ms_out, int64_t* launches_out, float* step_ms_out) {
     API_BEGIN(e)
     REQUIRE(e && slot && tokens && ms_out, B200RWKV_ERR_INVALID, "null argument");
     REQUIRE(nslot >= 1 && nslot <= e->S && nslot <= e->maxT && steps >= 1 && warmup >= 0, B200RWKV_ERR_INVALID, "bad argument");
@@ -2056,6 +2065,11 @@ int32_t b200rwkv_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_t* 
     cudaEvent_t ea, eb;
     CK(cudaEventCreate(&ea));
     CK(cudaEventCreate(&eb));
+    std::vector<cudaEvent_t> marks;            // per-step boundaries (optional): the distribution of the step time
+    if (step_ms_out) {
+        marks.resize(steps);
+        for (auto& m : marks) CK(cudaEventCreate(&m));
+    }
     const int MT = mt_bucket(nslot);
     for (int st = 0; st < nsteps; ++st) {
         if (st == warmup) {
@@ -2065,10 +2079,15 @@ int32_t b200rwkv_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_t* 
         if (flush) CK(cudaMemsetAsync(flush, st & 0xff, flush_bytes, e->stream));
         CK(cudaMemcpyAsync(e->d_meta, d_all + (size_t)st * e->meta_ints, e->meta_ints * 4, cudaMemcpyDeviceToDevice, e->stream));
         e->run_step(MT, MT);
+        if (step_ms_out && st >= warmup) CK(cudaEventRecord(marks[st - warmup], e->stream));
     }
     CK(cudaEventRecord(eb, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaEventElapsedTime(ms_out, ea, eb));
+    for (int i = 0; i < (int)marks.size(); ++i) {
+        CK(cudaEventElapsedTime(step_ms_out + i, i == 0 ? ea : marks[i - 1], marks[i]));
+    }
+    for (auto& m : marks) cudaEventDestroy(m);
     if (launches_out) *launches_out = (int64_t)e->launches_last_step * steps;   // counted when the step was enqueued / captured
     CK(cudaEventDestroy(ea));
     CK(cudaEventDestroy(eb));
@@ -2102,6 +2121,91 @@ int32_t b200rwkv_profile_step(b200rwkv_engine* e, int32_t nslot, const int32_t* 
         cudaEventDestroy(r.b);
     }
     if (gemm_weight_bytes) *gemm_weight_bytes = (int64_t)e->weight_bytes_total;
+    API_END
+}
+
+// In-situ timeline of a graph-replayed decode step: every launch of the step writes globaltimer stamps (CTA 0: entry, past
+// griddepcontrol.wait, exit; projections: exit of EVERY CTA).  A launch's window is [released by griddepcontrol.wait, last CTA
+// exit]: with programmatic dependent launch a kernel is resident long before it may touch its inputs, so CUDA events around
+// launches (b200rwkv_profile_step) over-count; windows of consecutive launches cannot overlap (the wait returns only when the
+// previous grid has completed), so their sum is <= the step.  Averages over `reps` replays of a traced copy of the step graph.
+int32_t b200rwkv_profile_insitu(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, int32_t reps,
+                                int32_t cap, int32_t* n_out, int32_t* types, double* start_us, double* end_us, int64_t* bytes,
+                                double* step_us) {
+    API_BEGIN(e)
+    REQUIRE(e && slot && tokens && n_out && types && start_us && end_us && bytes && step_us && reps >= 1 && cap >= 1, B200RWKV_ERR_INVALID,
+            "bad argument");
+    REQUIRE(nslot >= 1 && nslot <= e->S && nslot <= e->maxT, B200RWKV_ERR_INVALID, "bad argument");
+    REQUIRE(!e->mega_ok, B200RWKV_ERR_UNSUPPORTED, "in-situ profile: per-op chain only");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->dev));
+    if (!e->d_step_trace) e->d_step_trace = (unsigned long long*)e->dalloc((size_t)b200rwkv_engine::STEP_TRACE_MAX * b200rwkv_engine::STEP_TRACE_ROW * 8, true);
+    std::vector<int> all;
+    build_decode_metas(e, nslot, slot, tokens, 1, all);
+    CK(cudaMemcpyAsync(e->d_meta, all.data(), e->meta_ints * 4, cudaMemcpyHostToDevice, e->stream));
+    const int MT = mt_bucket(nslot);
+    // traced copy of the step graph (the production graphs carry null trace pointers)
+    const bool was = e->trace_capture;
+    e->trace_capture = true;
+    e->step_trace_types.clear();
+    e->step_trace_bytes.clear();
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ge = nullptr;
+    CK(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        e->enqueue_step(e->stream, MT, MT, nullptr);
+    } catch (...) {
+        cudaStreamEndCapture(e->stream, &g);
+        if (g) cudaGraphDestroy(g);
+        e->trace_capture = was;
+        throw;
+    }
+    e->trace_capture = was;
+    CK(cudaStreamEndCapture(e->stream, &g));
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    CK(cudaGraphDestroy(g));
+    const int n = (int)e->step_trace_types.size();
+    const size_t row = b200rwkv_engine::STEP_TRACE_ROW;
+    std::vector<unsigned long long> h((size_t)n * row);
+    std::vector<double> s_acc(n, 0.0), e_acc(n, 0.0);
+    double step_acc = 0.0;
+    e->step_trace_bytes.resize(n, 0);
+    for (int r = 0; r < reps + 1; ++r) {        // first replay is warm-up
+        CK(cudaMemsetAsync(e->d_step_trace, 0, (size_t)n * row * 8, e->stream));
+        CK(cudaGraphLaunch(ge, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        if (r == 0) continue;
+        CK(cudaMemcpy(h.data(), e->d_step_trace, (size_t)n * row * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull, t1 = 0;
+        for (int i = 0; i < n; ++i) {
+            const unsigned long long* q = h.data() + (size_t)i * row;
+            if (q[0] && q[0] < t0) t0 = q[0];
+        }
+        for (int i = 0; i < n; ++i) {
+            const unsigned long long* q = h.data() + (size_t)i * row;
+            const bool gemm = e->step_trace_types[i] >= 1000000;
+            unsigned long long st = gemm ? q[2] : q[1], en = q[7];
+            if (gemm)
+                for (int c = 0; c < e->num_sms && 8 + 3 * c + 2 < (int)row; ++c) en = std::max(en, q[8 + 3 * c + 2]);
+            if (!st || !en) continue;
+            s_acc[i] += (double)(st - t0) * 1e-3;
+            e_acc[i] += (double)(en - t0) * 1e-3;
+            t1 = std::max(t1, en);
+        }
+        step_acc += (double)(t1 - t0) * 1e-3;
+    }
+    cudaGraphExecDestroy(ge);
+    int m = 0;
+    for (int i = 0; i < n && m < cap; ++i) {
+        if (e_acc[i] <= 0.0) continue;
+        types[m] = e->step_trace_types[i];
+        start_us[m] = s_acc[i] / reps;
+        end_us[m] = e_acc[i] / reps;
+        bytes[m] = e->step_trace_bytes[i];
+        ++m;
+    }
+    *n_out = m;
+    *step_us = step_acc / reps;
     API_END
 }
 
@@ -2285,6 +2389,53 @@ int32_t b200rwkv_debug_stream(int32_t device, int32_t kind, double gbytes, int32
     *ms_out = ms / reps;
     CK(cudaFree(buf));
     CK(cudaFree(sink));
+    API_END
+}
+
+// L2 prefetch micro-benchmark (streamtest.cuh): per rep { flush L2 by streaming another buffer; prefetch kernel (+ idle);
+// timed streaming kernel }.  ms_out[0] = streaming kernel alone (events around it), ms_out[1] = prefetch + idle + stream.
+int32_t b200rwkv_debug_prefetch(int32_t device, double mbytes, int32_t consumers, int32_t pf_grid, int32_t skip, int32_t nblk,
+                                int32_t mode, double idle_us, int32_t reps, float* ms_out) {
+    API_BEGIN((b200rwkv_engine*)nullptr)
+    REQUIRE(ms_out && reps >= 1 && consumers >= 1 && pf_grid >= 1, B200RWKV_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(device));
+    const int stage = 32768, nstage = 5;
+    size_t per_cta = (size_t)(mbytes * 1e6 / consumers) / stage * stage;
+    const size_t total = per_cta * consumers;
+    const size_t flush_bytes = (size_t)148 * stage * 64;       // ~310 MB through the same ring kernel
+    uint8_t *buf = nullptr, *fl = nullptr;
+    CK(cudaMalloc(&buf, total + 1024));
+    CK(cudaMalloc(&fl, flush_bytes + 1024));
+    CK(cudaMemset(buf, 0, total));
+    CK(cudaMemset(fl, 0, flush_bytes));
+    const size_t smem = (size_t)nstage * stage + 2 * nstage * 8 + 64;
+    CK(cudaFuncSetAttribute(stream_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StreamParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.src = buf; sp.bytes_per_cta = per_cta; sp.stage_bytes = stage; sp.nstage = nstage; sp.use_hint = 1; sp.split = 1; sp.producers = 1;
+    StreamParams fp = sp;
+    fp.src = fl; fp.bytes_per_cta = (size_t)stage * 64;
+    cudaEvent_t a, b, c;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b)); CK(cudaEventCreate(&c));
+    double s0 = 0, s1 = 0;
+    for (int r = 0; r < reps + 1; ++r) {
+        stream_ring_kernel<<<148, 128, smem>>>(fp);
+        CK(cudaEventRecord(a));
+        prefetch_probe_kernel<<<pf_grid, 128>>>(buf, per_cta, consumers, skip, nblk, mode, (unsigned long long)(idle_us * 1e3));
+        CK(cudaEventRecord(b));
+        stream_ring_kernel<<<consumers, 128, smem>>>(sp);
+        CK(cudaEventRecord(c));
+        CK(cudaDeviceSynchronize());
+        CK(cudaGetLastError());
+        float m0 = 0.f, m1 = 0.f;
+        CK(cudaEventElapsedTime(&m0, b, c));
+        CK(cudaEventElapsedTime(&m1, a, c));
+        if (r > 0) { s0 += m0; s1 += m1; }
+    }
+    ms_out[0] = (float)(s0 / reps);
+    ms_out[1] = (float)(s1 / reps);
+    CK(cudaFree(buf)); CK(cudaFree(fl));
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c);
     API_END
 }
 

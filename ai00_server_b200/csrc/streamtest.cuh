@@ -102,4 +102,31 @@ __global__ void __launch_bounds__(128, 1) stream_ring_kernel(const __grid_consta
     if (warp == 1) tc_dealloc(tmem_base, 32);
 }
 
+// ---------------------------------------------------------------------------------------
+// L2 prefetch micro-benchmark (b200rwkv_debug_prefetch): does a prefetch issued while HBM is IDLE make the next streaming
+// launch faster?  Kernel P: CTA i asks L2 for `nblk` 32 KB blocks of the range consumer CTA i will stream (after its first
+// `skip` blocks), then idles `idle_ns`; kernel S = stream_ring_kernel over the same buffer.  mode 0: one thread, bulk
+// prefetches; 1: the 32 lanes of warp 0 issue them round robin; 2: every thread issues 128-byte prefetch.global.L2.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) prefetch_probe_kernel(const uint8_t* src, size_t bytes_per_cta, int consumers, int skip,
+                                                             int nblk, int mode, unsigned long long idle_ns) {
+    const unsigned long long t0 = globaltimer_ns();
+    for (int c = blockIdx.x; c < consumers; c += gridDim.x) {
+        const uint8_t* base = src + (size_t)c * bytes_per_cta + (size_t)skip * 32768;
+        const size_t avail = bytes_per_cta > (size_t)skip * 32768 ? (bytes_per_cta - (size_t)skip * 32768) / 32768 : 0;
+        const int n = (int)min((size_t)nblk, avail);
+        if (mode == 0) {
+            if (threadIdx.x == 0)
+                for (int i = 0; i < n; ++i) bulk_prefetch_l2(base + (size_t)i * 32768, 32768);
+        } else if (mode == 1) {
+            if (threadIdx.x < 32)
+                for (int i = threadIdx.x; i < n; i += 32) bulk_prefetch_l2(base + (size_t)i * 32768, 32768);
+        } else {
+            for (size_t off = (size_t)threadIdx.x * 128; off < (size_t)n * 32768; off += 128 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        }
+    }
+    while (globaltimer_ns() - t0 < idle_ns) { }
+}
+
 }  // namespace b200

@@ -315,9 +315,25 @@ class Model:
         assert tok.size == (warmup + steps) * len(slots)
         ms = C.c_float(0)
         launches = C.c_int64(0)
+        self.step_ms = np.zeros(steps, np.float32)          # CUDA-event time of every timed step (distribution)
         capi.check(capi.lib().b200rwkv_bench_decode(self._h, len(slots), capi.ptr(a_slot), capi.ptr(tok), warmup, steps,
-                                                    int(flush_l2), C.byref(ms), C.byref(launches)), self._h)
+                                                    int(flush_l2), C.byref(ms), C.byref(launches), capi.ptr(self.step_ms)), self._h)
         return ms.value, launches.value
+
+    def profile_insitu(self, slots, tokens, reps: int = 5):
+        """Per-launch windows of one graph-replayed decode step (b200rwkv_profile_insitu): list of dicts + step_us."""
+        a_slot = np.asarray(slots, np.int32)
+        tok = np.ascontiguousarray(tokens, dtype=np.uint32)
+        cap = 1024
+        n = C.c_int32(0)
+        types = np.zeros(cap, np.int32)
+        st, en = np.zeros(cap, np.float64), np.zeros(cap, np.float64)
+        by = np.zeros(cap, np.int64)
+        step = C.c_double(0)
+        capi.check(capi.lib().b200rwkv_profile_insitu(self._h, len(slots), capi.ptr(a_slot), capi.ptr(tok), reps, cap, C.byref(n),
+                                                      capi.ptr(types), capi.ptr(st), capi.ptr(en), capi.ptr(by), C.byref(step)), self._h)
+        k = n.value
+        return [{"type": int(types[i]), "start_us": float(st[i]), "end_us": float(en[i]), "bytes": int(by[i])} for i in range(k)], step.value
 
     def profile_step(self, slots, tokens):
         a_slot = np.asarray(slots, np.int32)

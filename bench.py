@@ -272,11 +272,16 @@ def main():
            "api": "runtime.Model.infer_raw -> b200rwkv_infer (host token ids in, host f32 logits out, wall clock)"}
 
     # ---- roofline of the dominant kernel (projection GEMM); SPMD under tensor parallelism ----
+    # In-situ windows of a graph-replayed step (globaltimer stamps written by the kernels: [wait released, last CTA exit]);
+    # consecutive windows cannot overlap, so the class sums are <= the step.  The un-graphed CUDA-event pass is kept beside
+    # it (`events_ungraphed`): it over-counts because programmatic dependent launch is off there.
     peaks, peak_src = read_peaks()
+    step_ms_dist = np.sort(np.asarray(model.step_ms, np.float64))
+    windows, insitu_step_us = model.profile_insitu(slots, dec[0], reps=5)
     prof_ms = np.zeros(4)
     prof_n = np.zeros(4, dtype=np.int64)
     wbytes = 0
-    reps = 5
+    reps = 3
     for i in range(reps + 1):
         m4, n4, wbytes = model.profile_step(slots, dec[i % dec.shape[0]])
         if i == 0:
@@ -288,29 +293,47 @@ def main():
         barrier()
         model.close()
         return
-    gemm_gbs = wbytes / (prof_ms[0] * 1e-3) / 1e9 if prof_ms[0] > 0 else 0.0
+    cls = {"gemm": [0.0, 0, 0], "wkv": [0.0, 0, 0], "ln_mix": [0.0, 0, 0], "front_half": [0.0, 0, 0]}
+    per_label = {}
+    for wdw in windows:
+        ty = wdw["type"]
+        name = "gemm" if ty >= 1000000 else {0: "ln_mix", 2: "wkv", 6: "front_half"}.get(ty, "ln_mix")
+        d = wdw["end_us"] - wdw["start_us"]
+        cls[name][0] += d; cls[name][1] += 1; cls[name][2] += wdw["bytes"]
+        lab = f"gemm_{ty - 1000000}MiB" if ty >= 1000000 else name
+        a = per_label.setdefault(lab, [0.0, 0, 0])
+        a[0] += d; a[1] += 1; a[2] += wdw["bytes"]
+    gemm_us, gemm_n, gemm_bytes = cls["gemm"]
+    gemm_gbs = gemm_bytes / (gemm_us * 1e-6) / 1e9 if gemm_us > 0 else 0.0
     alg_bytes = synth.algorithmic_bytes_per_step(shape, BATCH) / world
     traffic = None       # DRAM bytes of the same launches from the committed ncu capture (N = 1 capture of this workload)
     tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
     if world == 1 and PRESET == "v6-7b" and BATCH == 16 and os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic = tj["layers"] * sum(x["dram_bytes"] for x in tj["per_layer_gemm_launches"]) + tj["head"]["algorithmic_weight_bytes"]
-    roofline = {"bound": "hbm", "kernel": "gemm_kernel<1> (tcgen05 projection GEMM: all launches of one step, per GPU)",
+    windows_sum_us = sum(v[0] for v in cls.values())
+    roofline = {"bound": "hbm", "kernel": "gemm_kernel (tcgen05 projection GEMM: every launch of one step, per GPU)",
                 "achieved": gemm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gemm_gbs / peaks["hbm_gbs"],
                 "peak_source": f"MEASURED_PEAKS.json ({peak_src})", "traffic": traffic,
                 "traffic_note": "per step, summed over the same projection launches as `achieved`: ncu dram read+write bytes of one "
                                 "captured layer x 32 + the head's algorithmic bytes (profiles/r01_gemm_traffic.json)",
-                "algorithmic_bytes_per_step_gemm": int(wbytes), "gemm_ms_per_step": float(prof_ms[0]),
-                "gemm_launches_per_step": int(prof_n[0]),
-                "note": "per-launch CUDA events on the engine stream in an un-graphed pass (includes launch gaps); "
-                        "step_frac is the whole captured step against the same peak",
-                "class_ms_per_step": {"gemm": float(prof_ms[0]), "wkv": float(prof_ms[1]), "ln_mix": float(prof_ms[2]),
-                                      "other": float(prof_ms[3])},
-                "class_launches_per_step": {"gemm": int(prof_n[0]), "wkv": int(prof_n[1]), "ln_mix": int(prof_n[2]),
-                                            "other": int(prof_n[3])},
+                "how": "in situ: algorithmic weight bytes of the step's projection launches / sum of their windows [griddepcontrol.wait "
+                       "released, last CTA exit] inside a graph-replayed step (globaltimer stamps, mean of 5 replays)",
+                "algorithmic_bytes_per_step_gemm": int(gemm_bytes), "gemm_us_per_step": gemm_us, "gemm_launches_per_step": int(gemm_n),
+                "class_us_per_step": {k: v[0] for k, v in cls.items()},
+                "class_launches_per_step": {k: int(v[1]) for k, v in cls.items()},
+                "insitu_step_us": insitu_step_us, "windows_sum_us": windows_sum_us,
+                "between_windows_us": insitu_step_us - windows_sum_us,
+                "per_launch_class": {k: {"launches": int(v[1]), "avg_us": v[0] / max(v[1], 1),
+                                         "gbs": (v[2] / (v[0] * 1e-6) / 1e9) if v[2] and v[0] > 0 else None}
+                                     for k, v in sorted(per_label.items())},
+                "events_ungraphed": {"gemm_ms": float(prof_ms[0]), "wkv_ms": float(prof_ms[1]), "ln_mix_ms": float(prof_ms[2]),
+                                     "other_ms": float(prof_ms[3]), "launches": [int(x) for x in prof_n],
+                                     "note": "CUDA events around every launch of an un-graphed step without PDL: upper bounds"},
                 "step_algorithmic_bytes": int(alg_bytes),
                 "step_achieved_gbs": alg_bytes / (ms_per_step * 1e-3) / 1e9,
-                "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+                "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "step_ms_p10_p50_p90": [float(np.percentile(step_ms_dist, q)) for q in (10, 50, 90)] if step_ms_dist.size else None}
 
     # ---- cpu baseline (rank 0, N=1 only) ----
     cpu = None

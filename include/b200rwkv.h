@@ -153,12 +153,11 @@ void b200rwkv_host_free(void* p);
 /* Measurement hook used by bench.py for the kernel-resident number: runs `warmup + steps`
  * decode steps (one token per listed slot per step) with token ids staged in HBM beforehand,
  * no host<->device traffic inside the timed region; returns CUDA-event milliseconds for the
- * `steps` timed steps, the number of kernel launches in that region, and the device time
- * spent in the projection GEMM kernels (sum of per-launch event durations, measured in a
- * separate un-graphed pass of `gemm_probe_steps` steps; 0 to skip). */
+ * `steps` timed steps and the number of kernel launches in that region. */
 int32_t b200rwkv_bench_decode(b200rwkv_engine*, int32_t nslot, const int32_t* slot,
                               const uint32_t* tokens /* [(warmup+steps) * nslot] */, int32_t warmup,
-                              int32_t steps, int32_t flush_l2, float* ms_out, int64_t* launches_out);
+                              int32_t steps, int32_t flush_l2, float* ms_out, int64_t* launches_out,
+                              float* step_ms_out /* optional [steps]: CUDA-event time of every timed step */);
 
 /* Per-kernel-class device time of ONE un-graphed decode step, CUDA events around every launch
  * on the engine's stream.  classes: 0 = projection GEMMs, 1 = WKV, 2 = LN/mix/embed, 3 = other.
@@ -166,6 +165,15 @@ int32_t b200rwkv_bench_decode(b200rwkv_engine*, int32_t nslot, const int32_t* sl
 int32_t b200rwkv_profile_step(b200rwkv_engine*, int32_t nslot, const int32_t* slot,
                               const uint32_t* tokens, float ms[4], int32_t launches[4],
                               int64_t* gemm_weight_bytes);
+
+/* In-situ per-launch windows of ONE graph-replayed decode step (globaltimer stamps written by the kernels themselves):
+ * window = [griddepcontrol.wait released, last CTA exit]; consecutive windows cannot overlap, so class sums are <= the step.
+ * types[i]: 0 LN / mix, 2 WKV, 6 fused RWKV-6 front half, 1000000 + weight MiB for a projection launch; bytes[i]: algorithmic
+ * weight bytes of a projection launch (else 0); start_us / end_us relative to the first stamp of the step, averaged over
+ * `reps` replays; step_us = last exit - first entry.  bench.py's `roofline` comes from here. */
+int32_t b200rwkv_profile_insitu(b200rwkv_engine*, int32_t nslot, const int32_t* slot, const uint32_t* tokens, int32_t reps,
+                                int32_t cap, int32_t* n_out, int32_t* types, double* start_us, double* end_us, int64_t* bytes,
+                                double* step_us);
 
 /* Optional copy of the residual stream after the last layer for every token of the most
  * recent infer call ([T, C] f32) — the hidden state the documented embeddings route returns
@@ -192,6 +200,10 @@ int32_t b200rwkv_debug_gemm_time(b200rwkv_engine*, int32_t which, int32_t reps, 
 int32_t b200rwkv_debug_stream(int32_t device, int32_t kind, double gbytes, int32_t stage_bytes, int32_t nstage,
                               int32_t use_hint, int32_t consumer, int32_t split, int32_t producers, int32_t reps,
                               float* ms_out);
+
+/* Profiling aid: is an L2 prefetch issued while HBM idles still there when the next launch streams? (streamtest.cuh) */
+int32_t b200rwkv_debug_prefetch(int32_t device, double mbytes, int32_t consumers, int32_t pf_grid, int32_t skip, int32_t nblk,
+                                int32_t mode, double idle_us, int32_t reps, float* ms_out);
 
 const char* b200rwkv_last_error(b200rwkv_engine*);
 

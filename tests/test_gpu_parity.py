@@ -29,15 +29,15 @@ def rel_err(a, b):
 def models():
     cache = {}
 
-    def get(preset, seed=0, max_batch=4, chunk=32, mega=False, env=None, **over):
-        key = (preset, seed, max_batch, chunk, mega, tuple(sorted((env or {}).items())), tuple(sorted(over.items())))
+    def get(preset, seed=0, max_batch=4, chunk=32, mega=False, env=None, exact=False, **over):
+        key = (preset, seed, max_batch, chunk, mega, exact, tuple(sorted((env or {}).items())), tuple(sorted(over.items())))
         if key not in cache:
             shp = synth.PRESETS[preset] if not over else dataclasses.replace(synth.PRESETS[preset], **over)
             st = synth.make_st(shp, seed)
             os.environ["B200RWKV_MEGA"] = "1" if mega else "0"     # read at engine creation
             os.environ.update(env or {})
             try:
-                m = runtime.Model(st, max_batch=max_batch, token_chunk_size=chunk)
+                m = runtime.Model(st, max_batch=max_batch, token_chunk_size=chunk, exact=exact)
             finally:
                 os.environ.pop("B200RWKV_MEGA", None)
                 for k in (env or {}):
@@ -429,3 +429,28 @@ def test_experimental_split_operands_track_the_f32_oracle(models, preset):
             worst = max(worst, rel_err(rows[s], want))
             assert rows[s].argmax() == want.argmax()
     assert worst <= 1e-4, worst
+
+
+@pytest.mark.parametrize("dims", [dict(L=4, C=512, F=2048), dict(L=2, C=2560, F=10240)])
+@pytest.mark.parametrize("exact", [False, True])
+def test_v7_with_the_2b9_lora_ranks(models, exact, dims):
+    """RWKV-7 with the LoRA ranks of the 2.9B model (96 / 96 / 64 / 320: not multiples of the 128-wide k block, three k
+    blocks for the gate LoRA), at a depth where the 1e-3 bound still applies; both precisions; 8 slots like cfg 4."""
+    m, _, st = models("tiny7", max_batch=8, exact=exact, V=2048, Dd=96, Da=96, Dv=64, Dg=320, **dims)
+    orc = O.Oracle(O.parse_st(st), "f32" if exact else "f16")
+    rng = np.random.default_rng(31)
+    B = 8
+    sts = [orc.state_init() for _ in range(B)]
+    for s in range(B):
+        m.state.load(m.state.init(), s)
+    counts = [3, 1, 2, 1, 1, 4, 1, 2]
+    worst = 0.0
+    for step in range(4):
+        toks = [rng.integers(1, 2000, size=(n if step == 0 else 1)).tolist() for n in counts]
+        rows = m.infer_raw(list(range(B)), [len(t) for t in toks], sum(toks, []), [capi.OPTION_LAST] * B)
+        for s in range(B):
+            want, sts[s] = orc.run(toks[s], sts[s])
+            worst = max(worst, rel_err(rows[s], want))
+            assert rows[s].argmax() == want.argmax(), (step, s)
+    print(f"v7 2.9B ranks {dims} exact={exact}: worst rel {worst:.2e}")
+    assert worst <= (1e-4 if exact else REL_TOL), worst
