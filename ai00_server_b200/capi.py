@@ -54,6 +54,10 @@ SYMBOLS = [
     ("b200rwkv_state_read", C.c_int32, [_P, C.c_int32, C.POINTER(C.c_uint64)]),
     ("b200rwkv_state_write", C.c_int32, [_P, C.c_int32, C.c_uint64]),
     ("b200rwkv_state_free", C.c_int32, [_P, C.c_uint64]),
+    ("b200rwkv_snapshot_back", C.c_int32, [_P, C.c_uint64, _P, _P]),
+    ("b200rwkv_snapshot_load", C.c_int32, [_P, _P, _P, C.POINTER(C.c_uint64)]),
+    ("b200rwkv_cache_stats", C.c_int32, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("b200rwkv_read_state", C.c_int32, [C.POINTER(Info), _P, C.c_size_t, _P]),
     ("b200rwkv_softmax", C.c_int32, [_P, C.c_int32, _P, _P]),
     ("b200rwkv_sample_topk", C.c_int32, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P]),
     ("b200rwkv_host_alloc", C.c_int32, [C.c_size_t, C.POINTER(_P)]),

@@ -71,6 +71,7 @@ static std::string watchdog_report() {
 // safetensors reader (header = u64 LE length + JSON object; tensor bytes follow)
 // =========================================================================================
 struct StTensor {
+    std::string name;
     std::string dtype;
     std::vector<int64_t> shape;
     const uint8_t* data = nullptr;
@@ -148,6 +149,7 @@ public:
                 }
                 REQUIRE(ne <= ((uint64_t)1 << 44) && ne * esz == (uint64_t)t.nbytes, B200RWKV_ERR_INVALID,
                         "safetensors: byte length of " + key + " does not match dtype x shape");
+                t.name = key;
                 tensors.emplace(std::move(key), std::move(t));
             }
             ws();
@@ -291,6 +293,33 @@ static b200rwkv_info derive_info(const StFile& st) {
     return o;
 }
 
+static float st_elem_f32(const StTensor& t, size_t i) {
+    if (t.dtype == "F16") return __half2float(reinterpret_cast<const __half*>(t.data)[i]);
+    if (t.dtype == "F32") { float v; memcpy(&v, t.data + i * 4, 4); return v; }
+    if (t.dtype == "BF16") { uint32_t u = (uint32_t)reinterpret_cast<const uint16_t*>(t.data)[i] << 16; float v; memcpy(&v, &u, 4); return v; }
+    throw Error(B200RWKV_ERR_UNSUPPORTED, "tensor " + t.name + " is " + t.dtype + ", expected F16 / F32 / BF16");
+}
+
+// `vN::read_state` (reference lib.rs:378-389) and `State::init` with a state-tuned model (run.rs:477, lib.rs:452-462):
+// `blocks.{l}.att.time_state` [H, N, N] (transposed by the converter, convert_safetensors.py:101, crates/converter/src/main.rs:20)
+// -> the host state tensor [L][N+2][C]: row 1+i, column h*N+j <- time_state[h][i][j]; shift rows zero.
+// Returns false (and leaves `out` empty) when the file carries no time_state.
+static bool state_from_st(const StFile& st, int L, int H, int N, int C, std::vector<float>& out) {
+    if (!st.find("blocks.0.att.time_state")) return false;
+    out.assign((size_t)L * (N + 2) * C, 0.f);
+    for (int l = 0; l < L; ++l) {
+        const std::string name = "blocks." + std::to_string(l) + ".att.time_state";
+        const StTensor* ts = st.find(name);
+        REQUIRE(ts, B200RWKV_ERR_INVALID, "missing tensor: " + name);
+        REQUIRE(ts->numel() == (int64_t)H * N * N, B200RWKV_ERR_INVALID, "time_state must be [num_head, head_size, head_size]: " + name);
+        for (int h = 0; h < H; ++h)
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j)
+                    out[((size_t)l * (N + 2) + 1 + i) * C + h * N + j] = st_elem_f32(*ts, ((size_t)h * N + i) * N + j);
+    }
+    return true;
+}
+
 // =========================================================================================
 // engine
 // =========================================================================================
@@ -338,7 +367,7 @@ struct Profiler {
     std::vector<Rec> recs;
 };
 
-struct Snapshot { float* buf = nullptr; };
+struct Snapshot { float* buf = nullptr; float* logits = nullptr; size_t bytes = 0; };   // CachedItem {state, output} on the device (run.rs:199-205)
 
 }  // namespace b200
 
@@ -475,14 +504,14 @@ struct b200rwkv_engine {
                   const std::vector<int>& outmode /*0 none,1 last,2 full*/, int* R_out);
     void infer(int nslot, const int32_t* slot, const int32_t* ntok, const uint32_t* tokens, const int32_t* option,
                float* logits_out, size_t cap, int32_t* rows_out);
-    void state_xform(int slot, bool import);
+    void state_xform(int slot, bool import, float* snap = nullptr);
 };
 
 b200rwkv_engine::~b200rwkv_engine() {
     cudaSetDevice(dev);
     cudaDeviceSynchronize();
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
-    for (auto& kv : snaps) cudaFree(kv.second.buf);
+    for (auto& kv : snaps) { cudaFree(kv.second.buf); if (kv.second.logits) cudaFree(kv.second.logits); }
     for (void* p : allocs) cudaFree(p);
     if (d_tmp) cudaFree(d_tmp);          // only still set when build() threw
     if (sm_in) cudaFree(sm_in);
@@ -737,20 +766,7 @@ void b200rwkv_engine::build(const StFile& st) {
     ffn_shift = (float*)dalloc((size_t)L * S * C * 4);
     wkv_state = (float*)dalloc((size_t)L * S * Hl * N * N * 4);
     d_api = (float*)dalloc((size_t)L * (N + 2) * C * 4);
-    if (st.find("blocks.0.att.time_state")) {
-        // State::init() with a state-tuned model (reference run.rs:477, lib.rs:452-462): the converter
-        // stores time_state transposed ([H, N(i), N(j)], convert_safetensors.py:101); row 1+i, col h*N+j.
-        init_state.assign((size_t)L * (N + 2) * C, 0.f);
-        for (int l = 0; l < L; ++l) {
-            const StTensor& ts = st.get("blocks." + std::to_string(l) + ".att.time_state");
-            REQUIRE(ts.numel() == (int64_t)H * N * N, B200RWKV_ERR_INVALID, "time_state shape");
-            const __half* hp = reinterpret_cast<const __half*>(ts.data);
-            for (int h = 0; h < H; ++h)
-                for (int i = 0; i < N; ++i)
-                    for (int j = 0; j < N; ++j)
-                        init_state[((size_t)l * (N + 2) + 1 + i) * C + h * N + j] = __half2float(hp[((size_t)h * N + i) * N + j]);
-        }
-    }
+    state_from_st(st, L, H, N, C, init_state);      // State::init() with a state-tuned model; empty otherwise
 
     // ---- activations ----
     const size_t TC = (size_t)maxT * C, TCl = (size_t)maxT * Cl;
@@ -1705,10 +1721,21 @@ void b200rwkv_engine::sample_topk(int nrows, const int32_t* slots, const int32_t
     CK(cudaStreamSynchronize(sm_stream));
 }
 
-void b200rwkv_engine::state_xform(int slot, bool import) {
+// API layout <-> device layout for a live slot (snap == nullptr) or a snapshot record [L][C | Hl*N*N | C]
+void b200rwkv_engine::state_xform(int slot, bool import, float* snap) {
     StateXform x;
-    x.api = d_api; x.att_shift = att_shift; x.ffn_shift = ffn_shift; x.wkv = wkv_state;
-    x.L = L; x.C = C; x.S = S; x.Hl = Hl; x.h0 = rank * Hl; x.slot = slot; x.transpose = (info.version != 7);
+    const size_t W = (size_t)Hl * N * N;
+    x.api = d_api;
+    if (snap) {
+        const size_t rec = 2 * (size_t)C + W;
+        x.att = snap; x.wkv = snap + C; x.ffn = snap + C + W;
+        x.att_ls = x.wkv_ls = x.ffn_ls = rec;
+    } else {
+        x.att = att_shift + (size_t)slot * C; x.att_ls = (size_t)S * C;
+        x.ffn = ffn_shift + (size_t)slot * C; x.ffn_ls = (size_t)S * C;
+        x.wkv = wkv_state + (size_t)slot * W; x.wkv_ls = (size_t)S * W;
+    }
+    x.L = L; x.C = C; x.Hl = Hl; x.h0 = rank * Hl; x.transpose = (info.version != 7);
     const size_t total = (size_t)L * (N + 2) * C;
     const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
     if (import) state_xform_kernel<true><<<grid, 256, 0, stream>>>(x);
@@ -1944,17 +1971,43 @@ static void snapshot_copy(b200rwkv_engine* e, int slot, float* buf, bool to_snap
     }
 }
 
+// allocate a snapshot record (+ a logits row when this rank keeps them)
+static Snapshot snapshot_alloc(b200rwkv_engine* e, bool with_logits) {
+    Snapshot sn;
+    const size_t rec = 2 * (size_t)e->C + (size_t)e->Hl * e->N * e->N;
+    sn.bytes = rec * e->L * 4;
+    CK(cudaMalloc(&sn.buf, sn.bytes));
+    if (with_logits) {
+        cudaError_t ce = cudaMalloc(&sn.logits, (size_t)e->V * 4);
+        if (ce != cudaSuccess) { cudaFree(sn.buf); CK(ce); }
+        sn.bytes += (size_t)e->V * 4;
+    }
+    return sn;
+}
+
 int32_t b200rwkv_state_read(b200rwkv_engine* e, int32_t slot, uint64_t* snapshot_id) {
     API_BEGIN(e)
     REQUIRE(e && snapshot_id, B200RWKV_ERR_INVALID, "null argument");
     REQUIRE(slot >= 0 && slot < e->S, B200RWKV_ERR_STATE, "slot out of range");
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->dev));
-    Snapshot sn;
-    const size_t rec = 2 * (size_t)e->C + (size_t)e->Hl * e->N * e->N;
-    CK(cudaMalloc(&sn.buf, rec * e->L * 4));
-    snapshot_copy(e, slot, sn.buf, true);
-    CK(cudaStreamSynchronize(e->stream));
+    bool has_row;
+    {
+        std::lock_guard<std::mutex> lk2(e->keep_mu);
+        has_row = e->d_keep && e->keep_valid[slot];
+    }
+    Snapshot sn = snapshot_alloc(e, has_row);
+    try {
+        snapshot_copy(e, slot, sn.buf, true);
+        // the slot's last logits row travels with the state (CachedItem.output, run.rs:199-205): a cache hit can be sampled
+        // on the device without re-running the last token
+        if (has_row) CK(cudaMemcpyAsync(sn.logits, e->d_keep + (size_t)slot * e->V, (size_t)e->V * 4, cudaMemcpyDeviceToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    } catch (...) {
+        cudaFree(sn.buf);
+        if (sn.logits) cudaFree(sn.logits);
+        throw;
+    }
     const uint64_t id = e->next_snap++;
     e->snaps[id] = sn;
     *snapshot_id = id;
@@ -1970,7 +2023,14 @@ int32_t b200rwkv_state_write(b200rwkv_engine* e, int32_t slot, uint64_t snapshot
     REQUIRE(it != e->snaps.end(), B200RWKV_ERR_STATE, "unknown snapshot id");
     CK(cudaSetDevice(e->dev));
     snapshot_copy(e, slot, it->second.buf, false);
+    if (e->d_keep && it->second.logits)
+        CK(cudaMemcpyAsync(e->d_keep + (size_t)slot * e->V, it->second.logits, (size_t)e->V * 4, cudaMemcpyDeviceToDevice, e->stream));
+    CK(cudaEventRecord(e->step_done, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    {
+        std::lock_guard<std::mutex> lk2(e->keep_mu);
+        e->keep_valid[slot] = (e->d_keep && it->second.logits) ? 1 : 0;
+    }
     API_END
 }
 
@@ -1982,7 +2042,82 @@ int32_t b200rwkv_state_free(b200rwkv_engine* e, uint64_t snapshot_id) {
     REQUIRE(it != e->snaps.end(), B200RWKV_ERR_STATE, "unknown snapshot id");
     CK(cudaSetDevice(e->dev));
     CK(cudaFree(it->second.buf));
+    if (it->second.logits) CK(cudaFree(it->second.logits));
     e->snaps.erase(it);
+    API_END
+}
+
+// ---- device-resident state cache: snapshots <-> host tensors, without passing through a slot ----
+int32_t b200rwkv_snapshot_back(b200rwkv_engine* e, uint64_t snapshot_id, float* state_out, float* logits_out) {
+    API_BEGIN(e)
+    REQUIRE(e && (state_out || logits_out), B200RWKV_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    auto it = e->snaps.find(snapshot_id);
+    REQUIRE(it != e->snaps.end(), B200RWKV_ERR_STATE, "unknown snapshot id");
+    CK(cudaSetDevice(e->dev));
+    if (state_out) {
+        const size_t n = (size_t)e->L * (e->N + 2) * e->C;
+        e->state_xform(0, false, it->second.buf);
+        CK(cudaMemcpyAsync(state_out, e->d_api, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    }
+    if (logits_out) {
+        REQUIRE(it->second.logits, B200RWKV_ERR_STATE, "snapshot holds no logits row");
+        CK(cudaMemcpyAsync(logits_out, it->second.logits, (size_t)e->V * 4, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    API_END
+}
+
+int32_t b200rwkv_snapshot_load(b200rwkv_engine* e, const float* state_in, const float* logits_in, uint64_t* snapshot_id) {
+    API_BEGIN(e)
+    REQUIRE(e && state_in && snapshot_id, B200RWKV_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->dev));
+    Snapshot sn = snapshot_alloc(e, logits_in != nullptr && e->d_keep != nullptr);
+    try {
+        const size_t n = (size_t)e->L * (e->N + 2) * e->C;
+        CK(cudaMemcpyAsync(e->d_api, state_in, n * 4, cudaMemcpyHostToDevice, e->stream));
+        e->state_xform(0, true, sn.buf);
+        if (sn.logits) CK(cudaMemcpyAsync(sn.logits, logits_in, (size_t)e->V * 4, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+    } catch (...) {
+        cudaFree(sn.buf);
+        if (sn.logits) cudaFree(sn.logits);
+        throw;
+    }
+    const uint64_t id = e->next_snap++;
+    e->snaps[id] = sn;
+    *snapshot_id = id;
+    API_END
+}
+
+int32_t b200rwkv_cache_stats(b200rwkv_engine* e, int64_t* num_snapshots, int64_t* bytes_used, int64_t* bytes_free) {
+    API_BEGIN(e)
+    REQUIRE(e, B200RWKV_ERR_INVALID, "null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
+    CK(cudaSetDevice(e->dev));
+    int64_t used = 0;
+    for (auto& kv : e->snaps) used += (int64_t)kv.second.bytes;
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot));
+    if (num_snapshots) *num_snapshots = (int64_t)e->snaps.size();
+    if (bytes_used) *bytes_used = used;
+    if (bytes_free) *bytes_free = (int64_t)fr;
+    API_END
+}
+
+// `vN::read_state(&context, &info, reader)` (reference lib.rs:378-389; `.state` files and InputState::File, run.rs:403-437):
+// host only.  out: [L][N+2][C] f32 in the web-rwkv state layout.
+int32_t b200rwkv_read_state(const b200rwkv_info* info, const uint8_t* st, size_t len, float* out) {
+    API_BEGIN((b200rwkv_engine*)nullptr)
+    REQUIRE(info && out, B200RWKV_ERR_INVALID, "null argument");
+    REQUIRE(info->num_layer > 0 && info->num_head > 0 && info->head_size > 0 && info->num_emb == info->num_head * info->head_size,
+            B200RWKV_ERR_INVALID, "bad model info");
+    StFile f(st, len);
+    std::vector<float> v;
+    REQUIRE(state_from_st(f, info->num_layer, info->num_head, info->head_size, info->num_emb, v), B200RWKV_ERR_INVALID,
+            "no blocks.*.att.time_state tensors in this file");
+    memcpy(out, v.data(), v.size() * 4);
     API_END
 }
 

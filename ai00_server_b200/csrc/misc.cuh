@@ -34,10 +34,11 @@ __global__ void __launch_bounds__(1024) softmax_kernel(const float* __restrict__
 // ---------------------------------------------------------------------------------------
 struct StateXform {
     float* api;          // [L][N+2][C] staging in HBM
-    float* att_shift;    // [L][S][C]
-    float* ffn_shift;    // [L][S][C]
-    float* wkv;          // [L][S][Hl][64][64]
-    int L, C, S, Hl, h0, slot, transpose;
+    // device side, addressed as base + l * layer_stride: a slot of the live state arrays or a snapshot record
+    float* att; size_t att_ls;     // [C] per layer
+    float* ffn; size_t ffn_ls;     // [C] per layer
+    float* wkv; size_t wkv_ls;     // [Hl][64][64] per layer
+    int L, C, Hl, h0, transpose;
 };
 
 template <bool IMPORT>
@@ -51,8 +52,8 @@ __global__ void state_xform_kernel(const StateXform p) {
         const int row = (int)(r / p.C);
         const int c = (int)(r - (size_t)row * p.C);
         float* dev;
-        if (row == 0) dev = p.att_shift + ((size_t)l * p.S + p.slot) * p.C + c;
-        else if (row == N + 1) dev = p.ffn_shift + ((size_t)l * p.S + p.slot) * p.C + c;
+        if (row == 0) dev = p.att + (size_t)l * p.att_ls + c;
+        else if (row == N + 1) dev = p.ffn + (size_t)l * p.ffn_ls + c;
         else {
             const int hg = c / N, j = c % N, ii = row - 1;
             const int hl = hg - p.h0;
@@ -61,7 +62,7 @@ __global__ void state_xform_kernel(const StateXform p) {
                 continue;
             }
             const int val = p.transpose ? j : ii, key = p.transpose ? ii : j;
-            dev = p.wkv + ((((size_t)l * p.S + p.slot) * p.Hl + hl) * N + val) * N + key;
+            dev = p.wkv + (size_t)l * p.wkv_ls + ((size_t)hl * N + val) * N + key;
         }
         if (IMPORT) *dev = p.api[i];
         else p.api[i] = *dev;

@@ -60,6 +60,15 @@ class Loader:
         return capi.info_from_st(st)
 
 
+def read_state(info: dict, st: np.ndarray) -> np.ndarray:
+    """`vN::read_state(&context, &info, reader)` (lib.rs:378-389): `.state` file / state-tuned model -> state tensor."""
+    st = np.ascontiguousarray(st, dtype=np.uint8)
+    ci = capi.Info(**{k: int(v) for k, v in info.items()})
+    out = np.empty((info["num_layer"], info["head_size"] + 2, info["num_emb"]), np.float32)
+    capi.check(capi.lib().b200rwkv_read_state(C.byref(ci), capi.ptr(st), st.size, capi.ptr(out)))
+    return out
+
+
 class TensorGpu:
     """Device-side state snapshot handle (`TensorGpu<f32, ReadWrite>` at run.rs:1104-1108)."""
 
@@ -112,6 +121,27 @@ class State:
 
     def write(self, tensor: TensorGpu, batch: int) -> None:
         capi.check(capi.lib().b200rwkv_state_write(self._m._h, batch, tensor.id), self._m._h)
+
+    # ---- device-resident cache items (CachedItem {state, output}, run.rs:199-205) ----
+    def snapshot_back(self, tensor: TensorGpu, with_logits: bool = False):
+        out = np.empty(self._np_shape(), np.float32)
+        lg = np.empty(self._m.info["num_vocab"], np.float32) if with_logits else None
+        capi.check(capi.lib().b200rwkv_snapshot_back(self._m._h, tensor.id, capi.ptr(out), capi.ptr(lg) if with_logits else None), self._m._h)
+        return (out, lg) if with_logits else out
+
+    def snapshot_load(self, tensor: np.ndarray, logits: np.ndarray | None = None) -> TensorGpu:
+        t = np.ascontiguousarray(tensor, dtype=np.float32)
+        if t.size != self._numel():
+            raise capi.B200Error(capi.ERR_INVALID, "state tensor has the wrong number of elements")
+        lg = None if logits is None else np.ascontiguousarray(logits, dtype=np.float32)
+        sid = C.c_uint64(0)
+        capi.check(capi.lib().b200rwkv_snapshot_load(self._m._h, capi.ptr(t), capi.ptr(lg) if lg is not None else None, C.byref(sid)), self._m._h)
+        return TensorGpu(self._m, sid.value)
+
+    def cache_stats(self) -> dict:
+        n, used, free = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        capi.check(capi.lib().b200rwkv_cache_stats(self._m._h, C.byref(n), C.byref(used), C.byref(free)), self._m._h)
+        return {"snapshots": n.value, "bytes_used": used.value, "bytes_free": free.value}
 
 
 class NucleusSampler:

@@ -114,10 +114,12 @@ def host_threads() -> int:
         return max(1, int(os.environ["B200RWKV_CPU_THREADS"]))
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     try:
+        # SMT present -> one thread per core = half of the usable logical CPUs.  (The absolute core count virtualised hosts
+        # report is not trusted: the GPU box says 16 cores / 128 logical CPUs, where 64 threads measured fastest.)
         import psutil
         phys, logical = psutil.cpu_count(logical=False), psutil.cpu_count(logical=True)
         if phys and logical and logical > phys:
-            n = max(1, min(phys, n * phys // logical))
+            n = max(1, n // 2)
     except Exception:
         pass
     try:

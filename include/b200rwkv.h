@@ -122,6 +122,23 @@ int32_t b200rwkv_state_read(b200rwkv_engine*, int32_t slot, uint64_t* snapshot_i
 int32_t b200rwkv_state_write(b200rwkv_engine*, int32_t slot, uint64_t snapshot_id);  /* State::write */
 int32_t b200rwkv_state_free(b200rwkv_engine*, uint64_t snapshot_id);                 /* drop TensorGpu */
 
+/* Device-resident state cache.  The reference's cache holds `CachedItem { state: TensorCpu, output:
+ * TensorCpu }` (crates/ai00-core/src/run.rs:199-205): every check-out / check-in is a State::load / State::back PCIe copy of
+ * the whole state (34.6 MB per slot at 7B; run.rs:838, 996, 561).  Here a cached item is a snapshot id: state_read /
+ * state_write are device-to-device copies, and the snapshot carries the slot's last logits row with it, so a cache hit can
+ * be sampled on the device (b200rwkv_sample_topk) without re-running a token.  The two calls below move a snapshot to / from
+ * host tensors without occupying a slot -- for spilling under memory pressure (b200rwkv_cache_stats), for `InputState::Value`
+ * / `.state` files (run.rs:390-437) and for `/api/oai/states` (run.rs:984-989).  state: [C, N+2, L, 1] f32 as in
+ * b200rwkv_state_back; logits: [num_vocab] f32, either pointer may be NULL (logits_out: ERR_STATE if the snapshot has no row). */
+int32_t b200rwkv_snapshot_back(b200rwkv_engine*, uint64_t snapshot_id, float* state_out, float* logits_out);
+int32_t b200rwkv_snapshot_load(b200rwkv_engine*, const float* state_in, const float* logits_in, uint64_t* snapshot_id);
+int32_t b200rwkv_cache_stats(b200rwkv_engine*, int64_t* num_snapshots, int64_t* bytes_used, int64_t* bytes_free);
+
+/* Replaces `vN::read_state(&context, &info, reader)` — crates/ai00-core/src/lib.rs:378-389 (initial states of state-tuned
+ * models and `.state` files, run.rs:403-437): reads `blocks.{l}.att.time_state` [H, N, N] (F16 / F32 / BF16; the layout the
+ * converter writes, crates/converter/src/main.rs:20) into the state tensor `out` ([C, N+2, L, 1] f32).  Host only. */
+int32_t b200rwkv_read_state(const b200rwkv_info* info, const uint8_t* st, size_t len, float* out);
+
 /* Replaces `web_rwkv::runtime::softmax::softmax(&context, Vec<TensorCpu<f32>>)` —
  * crates/ai00-core/src/run.rs:1179.  in/out: [rows, num_vocab] f32. */
 int32_t b200rwkv_softmax(b200rwkv_engine*, int32_t rows, const float* in, float* out);

@@ -137,3 +137,33 @@ def test_runtime_chunking_bookkeeping():
     assert seen_rows == {0: 1, 2: 2}
     assert calls[0] == ([0], [4], [1, 2, 3, 4], [capi.OPTION_NONE])
     assert calls[1] == ([0, 2], [1, 2], [5, 7, 8], [capi.OPTION_LAST, capi.OPTION_FULL])
+
+
+def test_read_state_host_only():
+    """`vN::read_state` (reference lib.rs:378-389): a state-tuned model / `.state` file -> the [L, N+2, C] state tensor; the
+    oracle builds the same tensor from the same file (row 1+i, column h*N+j <- time_state[h][i][j])."""
+    import dataclasses
+    import json
+    import struct
+    from oracle import rwkv_numpy as O
+    shp = dataclasses.replace(synth.PRESETS["tiny6"], time_state=True)
+    st = synth.make_st(shp, 0)
+    info = capi.info_from_st(st)
+    got = runtime.read_state(info, st)
+    want = O.Oracle(O.parse_st(st), "f16").state_init()
+    assert got.shape == want.shape and np.array_equal(got, want) and np.abs(got[:, 1:65]).max() > 0
+    assert np.all(got[:, 0] == 0) and np.all(got[:, 65] == 0)
+    # a stand-alone `.state` file: only the time_state tensors, stored as F32
+    w = O.parse_st(st)
+    names = [n for n in w if n.endswith("att.time_state")]
+    hdr, blobs, off = {"__metadata__": {"format": "pt"}}, [], 0
+    for n in names:
+        b = w[n].astype(np.float32).tobytes()
+        hdr[n] = {"dtype": "F32", "shape": list(w[n].shape), "data_offsets": [off, off + len(b)]}
+        blobs.append(b); off += len(b)
+    h = json.dumps(hdr).encode()
+    img = np.frombuffer(struct.pack("<Q", len(h)) + h + b"".join(blobs), np.uint8).copy()
+    assert np.array_equal(runtime.read_state(info, img), want)
+    with pytest.raises(capi.B200Error) as ei:           # a model without time_state is not a state file
+        runtime.read_state(info, synth.make_st("tiny6", 0))
+    assert ei.value.code == capi.ERR_INVALID

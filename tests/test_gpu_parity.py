@@ -454,3 +454,34 @@ def test_v7_with_the_2b9_lora_ranks(models, exact, dims):
             assert rows[s].argmax() == want.argmax(), (step, s)
     print(f"v7 2.9B ranks {dims} exact={exact}: worst rel {worst:.2e}")
     assert worst <= (1e-4 if exact else REL_TOL), worst
+
+
+def test_device_resident_state_cache(models):
+    """CachedItem {state, output} as device snapshots: read / write are D2D and carry the slot's last logits
+    row; snapshot_back / snapshot_load move a cached item to / from host tensors without occupying a slot."""
+    m, orc, _ = models("tiny6")
+    m.state.load(m.state.init(), 0)
+    rows = m.infer_raw([0], [4], [3, 4, 5, 6], [capi.OPTION_LAST])[0]
+    before = m.state.back(0)
+    n0 = m.state.cache_stats()["snapshots"]
+    snap = m.state.read(0)
+    st = m.state.cache_stats()
+    assert st["snapshots"] == n0 + 1 and st["bytes_used"] > 0 and st["bytes_free"] > 0
+    host_state, host_logits = m.state.snapshot_back(snap, with_logits=True)
+    assert np.array_equal(host_state, before) and np.array_equal(host_logits, rows[0])
+    # a cache hit on another slot: state and the last logits row arrive together, the GPU sampler works without a re-run
+    m.state.write(snap, 2)
+    assert np.array_equal(m.state.back(2), before)
+    ids, _ = m.sample_topk([2], top_k=3)
+    assert ids[0, 0] == rows[0].argmax()
+    # host tensor -> device snapshot (InputState::Value / a .state file), then into a slot
+    rng = np.random.default_rng(12)
+    ext = rng.standard_normal(before.shape).astype(np.float32)
+    snap2 = m.state.snapshot_load(ext)
+    assert np.array_equal(m.state.snapshot_back(snap2), ext)
+    m.state.write(snap2, 1)
+    assert np.array_equal(m.state.back(1), ext)
+    with pytest.raises(capi.B200Error):
+        m.sample_topk([1], top_k=3)                  # that snapshot carried no logits row
+    snap.free(); snap2.free()
+    assert m.state.cache_stats()["snapshots"] == n0
