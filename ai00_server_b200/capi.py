@@ -29,6 +29,16 @@ class Info(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+MAX_LORA = 4
+
+
+class Options(C.Structure):
+    """b200rwkv_options (include/b200rwkv.h)."""
+    _fields_ = [("struct_bytes", C.c_uint32), ("max_batch", C.c_int32), ("token_chunk_size", C.c_int32), ("precision", C.c_int32),
+                ("num_devices", C.c_int32), ("devices", C.c_int32 * 8), ("num_lora", C.c_int32),
+                ("lora_st", C.c_void_p * MAX_LORA), ("lora_len", C.c_size_t * MAX_LORA), ("lora_alpha", C.c_float * MAX_LORA)]
+
+
 class B200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"b200rwkv error {code}: {msg}")
@@ -40,6 +50,7 @@ _P = C.c_void_p
 SYMBOLS = [
     ("b200rwkv_info_from_st", C.c_int32, [_P, C.c_size_t, C.POINTER(Info)]),
     ("b200rwkv_create", C.c_int32, [_P, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    ("b200rwkv_create_ex", C.c_int32, [_P, C.c_size_t, C.POINTER(Options), C.POINTER(_P)]),
     ("b200rwkv_create_tp", C.c_int32, [_P, C.c_size_t, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
     ("b200rwkv_tp_export", C.c_int32, [_P, _P]),
     ("b200rwkv_tp_connect", C.c_int32, [_P, _P]),

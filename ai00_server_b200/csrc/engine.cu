@@ -6,6 +6,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -373,7 +376,30 @@ struct Snapshot { float* buf = nullptr; float* logits = nullptr; size_t bytes = 
 
 using namespace b200;
 
+// In-process tensor parallelism (b200rwkv_create_ex with num_devices > 1): the handle the host holds is rank 0's engine; it
+// owns the other ranks and one worker thread per rank.  Every SPMD entry point fans out to all ranks CONCURRENTLY (the ranks'
+// kernels rendezvous with each other over NVLink, so one thread issuing rank after rank would deadlock on its first
+// stream synchronisation) and returns rank 0's result: the reference's single `Runtime` object (run.rs:1230-1234).
+struct Group {
+    std::vector<b200rwkv_engine*> ranks;      // [world]; ranks[0] is the handle itself
+    std::vector<std::thread> workers;         // ranks 1..world-1 (rank 0's share runs on the calling thread)
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int32_t(int)> job;
+    uint64_t gen = 0;
+    int pending = 0;
+    bool stop = false;
+    std::vector<int32_t> status;
+    std::vector<std::string> errs;
+    std::mutex call_mu;                       // one fan-out at a time
+
+    void start(int world);
+    void shutdown();
+    int32_t spmd(const std::function<int32_t(int)>& fn);
+};
+
 struct b200rwkv_engine {
+    std::unique_ptr<Group> group;             // set on rank 0 of an in-process tensor-parallel engine
     b200rwkv_info info;
     int dev = 0, rank = 0, world = 1, num_sms = 148;
     int S = 0, chunk = 0, maxT = 64, precision = 0;
@@ -443,6 +469,12 @@ struct b200rwkv_engine {
                      int top_k, uint32_t* ids_out, float* probs_out);
 
     std::mutex mu, sm_mu;
+
+    // LoRA files blended into the projection weights while they are uploaded (borrowed during build only)
+    struct LoraSrc { const StFile* st; float alpha; };
+    std::vector<LoraSrc> loras;
+    void check_loras(const StFile& model) const;
+    void blend_loras(const StTensor& t);
 
     // temp upload buffer during build
     __half* d_tmp = nullptr;
@@ -550,8 +582,59 @@ const __half* b200rwkv_engine::upload_tmp(const StTensor& t) {
         REQUIRE(t.nbytes <= d_tmp_bytes, B200RWKV_ERR_INVALID, "internal: temp buffer too small");
         CK(cudaMemcpy(d_tmp, t.data, t.nbytes, cudaMemcpyHostToDevice));
         d_tmp_holds = &t;
+        blend_loras(t);
     }
     return d_tmp;
+}
+
+static bool ends_with(const std::string& s, const std::string& suf) {
+    return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+
+// Every `<base>.lora.0/.lora.1` pair of a LoRA file must address a projection matrix this engine blends (the matrices that
+// go through upload_tmp); anything else is refused loudly rather than ignored.
+void b200rwkv_engine::check_loras(const StFile& model) const {
+    static const char* ok[] = {".att.receptance", ".att.key", ".att.value", ".att.gate", ".att.output", ".ffn.key", ".ffn.value", ".ffn.receptance"};
+    for (const LoraSrc& lo : loras) {
+        int pairs = 0;
+        for (auto& kv : lo.st->tensors) {
+            const std::string& n = kv.first;
+            if (ends_with(n, ".lora.1")) continue;
+            if (!ends_with(n, ".lora.0")) {
+                REQUIRE(!model.find(n), B200RWKV_ERR_UNSUPPORTED, "LoRA file carries a full tensor (" + n + "): only low-rank pairs on projection matrices are blended");
+                continue;
+            }
+            const std::string base = n.substr(0, n.size() - 7);
+            bool good = (base == "head");
+            for (const char* o : ok) good = good || ends_with(base, o);
+            REQUIRE(good && model.find(base + ".weight"), B200RWKV_ERR_UNSUPPORTED, "LoRA on " + base + " is not supported (projection matrices only)");
+            REQUIRE(lo.st->find(base + ".lora.1"), B200RWKV_ERR_INVALID, "LoRA file: " + base + ".lora.1 is missing");
+            ++pairs;
+        }
+        REQUIRE(pairs > 0, B200RWKV_ERR_INVALID, "LoRA file holds no <name>.lora.0 / <name>.lora.1 pairs");
+    }
+}
+
+void b200rwkv_engine::blend_loras(const StTensor& t) {
+    if (loras.empty() || !ends_with(t.name, ".weight") || t.shape.size() != 2) return;
+    const std::string base = t.name.substr(0, t.name.size() - 7);
+    const int out = (int)t.shape[0], in = (int)t.shape[1];
+    for (const LoraSrc& lo : loras) {
+        const StTensor* a = lo.st->find(base + ".lora.0");
+        const StTensor* b = lo.st->find(base + ".lora.1");
+        if (!a || !b) continue;
+        REQUIRE(a->dtype == "F16" && b->dtype == "F16", B200RWKV_ERR_UNSUPPORTED, "LoRA tensors must be F16: " + base);
+        REQUIRE(a->shape.size() == 2 && b->shape.size() == 2 && b->shape[0] == out && a->shape[0] == in && a->shape[1] == b->shape[1] &&
+                    a->shape[1] >= 1 && a->shape[1] <= 4096,
+                B200RWKV_ERR_INVALID, "LoRA shapes do not match " + t.name + " (expected lora.0 [in, r], lora.1 [out, r])");
+        const int r = (int)a->shape[1];
+        DevTmp da(a->nbytes), db(b->nbytes);
+        CK(cudaMemcpy(da.p, a->data, a->nbytes, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(db.p, b->data, b->nbytes, cudaMemcpyHostToDevice));
+        lora_blend_kernel<<<148 * 8, 256>>>(d_tmp, (const __half*)db.p, (const __half*)da.p, out, in, r, lo.alpha);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
 }
 
 float* b200rwkv_engine::vec_f32(const StFile& st, const std::string& name, size_t off, size_t count, float scale, float bias) {
@@ -716,6 +799,7 @@ int b200rwkv_engine::pick_split(int K, int tiles) const {
 // -----------------------------------------------------------------------------------------
 void b200rwkv_engine::build(const StFile& st) {
     info = derive_info(st);
+    check_loras(st);
     L = info.num_layer; C = info.num_emb; F = info.num_hidden; V = info.num_vocab; H = info.num_head; N = info.head_size;
     REQUIRE(N == 64, B200RWKV_ERR_UNSUPPORTED, "head_size must be 64");
     REQUIRE(H * N == C, B200RWKV_ERR_UNSUPPORTED, "num_head * head_size must equal num_emb");
@@ -1744,6 +1828,82 @@ void b200rwkv_engine::state_xform(int slot, bool import, float* snap) {
 }
 
 // =========================================================================================
+// in-process tensor-parallel group
+// =========================================================================================
+void Group::start(int world) {
+    status.assign(world, 0);
+    errs.assign(world, "");
+    for (int r = 1; r < world; ++r)
+        workers.emplace_back([this, r]() {
+            uint64_t seen = 0;
+            for (;;) {
+                std::function<int32_t(int)> fn;
+                {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [&] { return stop || gen != seen; });
+                    if (stop) return;
+                    seen = gen;
+                    fn = job;
+                }
+                int32_t st;
+                try {
+                    st = fn(r);
+                } catch (const std::exception& ex) {
+                    g_err = ex.what();
+                    st = B200RWKV_ERR_INVALID;
+                }
+                {
+                    std::lock_guard<std::mutex> lk(m);
+                    status[r] = st;
+                    errs[r] = st < 0 ? g_err : std::string();
+                    --pending;
+                }
+                cv.notify_all();
+            }
+        });
+}
+
+void Group::shutdown() {
+    {
+        std::lock_guard<std::mutex> lk(m);
+        stop = true;
+    }
+    cv.notify_all();
+    for (auto& t : workers) t.join();
+    workers.clear();
+}
+
+// run fn(rank) on every rank at once; the first failure (lowest rank) is what the caller sees
+int32_t Group::spmd(const std::function<int32_t(int)>& fn) {
+    std::lock_guard<std::mutex> call(call_mu);
+    {
+        std::lock_guard<std::mutex> lk(m);
+        job = fn;
+        pending = (int)workers.size();
+        ++gen;
+    }
+    cv.notify_all();
+    int32_t st0;
+    try {
+        st0 = fn(0);
+    } catch (const std::exception& ex) {
+        g_err = ex.what();
+        st0 = B200RWKV_ERR_INVALID;
+    }
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return pending == 0; });
+    }
+    if (st0 < 0) return st0;
+    for (size_t r = 1; r < status.size(); ++r)
+        if (status[r] < 0) {
+            g_err = "rank " + std::to_string(r) + ": " + errs[r];
+            return status[r];
+        }
+    return st0;
+}
+
+// =========================================================================================
 // C ABI
 // =========================================================================================
 // Error text is thread-local: the reference makes engine calls from two tasks (infer / softmax, run.rs:1232-1237) and a
@@ -1778,8 +1938,10 @@ int32_t b200rwkv_info_from_st(const uint8_t* st, size_t len, b200rwkv_info* out)
     API_END
 }
 
-int32_t b200rwkv_create_tp(const uint8_t* st, size_t len, int32_t device, int32_t max_batch, int32_t token_chunk_size,
-                           int32_t precision, int32_t rank, int32_t world, b200rwkv_engine** out) {
+struct LoraArg { const uint8_t* st; size_t len; float alpha; };
+
+static int32_t create_rank(const uint8_t* st, size_t len, int32_t device, int32_t max_batch, int32_t token_chunk_size,
+                           int32_t precision, int32_t rank, int32_t world, const std::vector<LoraArg>& lora, b200rwkv_engine** out) {
     API_BEGIN((b200rwkv_engine*)nullptr)
     REQUIRE(out, B200RWKV_ERR_INVALID, "null out");
     *out = nullptr;
@@ -1805,7 +1967,13 @@ int32_t b200rwkv_create_tp(const uint8_t* st, size_t len, int32_t device, int32_
     REQUIRE(prop.major == 10, B200RWKV_ERR_UNSUPPORTED,
             "this library is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
     StFile f(st, len);
+    std::vector<std::unique_ptr<StFile>> lora_files;
     std::unique_ptr<b200rwkv_engine> e(new b200rwkv_engine());
+    for (const LoraArg& la : lora) {
+        REQUIRE(la.st && la.len > 8, B200RWKV_ERR_INVALID, "null LoRA image");
+        lora_files.emplace_back(new StFile(la.st, la.len));
+        e->loras.push_back({lora_files.back().get(), la.alpha});
+    }
     e->dev = device; e->rank = rank; e->world = world; e->num_sms = prop.multiProcessorCount;
     e->S = max_batch; e->chunk = token_chunk_size; e->precision = precision;
     if (const char* v = getenv("B200RWKV_GRAPH")) e->use_graph = atoi(v) != 0;
@@ -1813,13 +1981,19 @@ int32_t b200rwkv_create_tp(const uint8_t* st, size_t len, int32_t device, int32_
     if (const char* v = getenv("B200RWKV_SKIP")) e->skip_mask = atoi(v);
     if (const char* v = getenv("B200RWKV_MEGA")) e->use_mega = atoi(v) != 0;
     e->build(f);
+    e->loras.clear();            // the LoRA images are only borrowed during the build
     *out = e.release();
     API_END
 }
 
+int32_t b200rwkv_create_tp(const uint8_t* st, size_t len, int32_t device, int32_t max_batch, int32_t token_chunk_size,
+                           int32_t precision, int32_t rank, int32_t world, b200rwkv_engine** out) {
+    return create_rank(st, len, device, max_batch, token_chunk_size, precision, rank, world, {}, out);
+}
+
 int32_t b200rwkv_create(const uint8_t* st, size_t len, int32_t device, int32_t max_batch, int32_t token_chunk_size,
                         int32_t precision, b200rwkv_engine** out) {
-    return b200rwkv_create_tp(st, len, device, max_batch, token_chunk_size, precision, 0, 1, out);
+    return create_rank(st, len, device, max_batch, token_chunk_size, precision, 0, 1, {}, out);
 }
 
 struct TpHandle {            // wire format of the 128-byte blob
@@ -1896,7 +2070,15 @@ int32_t b200rwkv_tp_connect_local(b200rwkv_engine** engines, int32_t n) {
     API_END
 }
 
-void b200rwkv_destroy(b200rwkv_engine* e) { delete e; }
+void b200rwkv_destroy(b200rwkv_engine* e) {
+    if (!e) return;
+    if (e->group) {
+        std::unique_ptr<Group> g = std::move(e->group);
+        g->shutdown();
+        for (size_t r = 1; r < g->ranks.size(); ++r) delete g->ranks[r];
+    }
+    delete e;
+}
 
 int32_t b200rwkv_get_info(b200rwkv_engine* e, b200rwkv_info* out) {
     API_BEGIN(e)
@@ -1905,7 +2087,7 @@ int32_t b200rwkv_get_info(b200rwkv_engine* e, b200rwkv_info* out) {
     API_END
 }
 
-int32_t b200rwkv_infer(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const int32_t* ntok, const uint32_t* tokens,
+static int32_t rank_infer(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const int32_t* ntok, const uint32_t* tokens,
                        const int32_t* option, float* logits_out, size_t logits_cap, int32_t* rows_out) {
     API_BEGIN(e)
     REQUIRE(e, B200RWKV_ERR_INVALID, "null engine");
@@ -1931,7 +2113,7 @@ int32_t b200rwkv_state_init(b200rwkv_engine* e, float* out) {
     API_END
 }
 
-int32_t b200rwkv_state_load(b200rwkv_engine* e, int32_t slot, const float* in) {
+static int32_t rank_state_load(b200rwkv_engine* e, int32_t slot, const float* in) {
     API_BEGIN(e)
     REQUIRE(e && in, B200RWKV_ERR_INVALID, "null argument");
     REQUIRE(slot >= 0 && slot < e->S, B200RWKV_ERR_STATE, "slot out of range");
@@ -1944,7 +2126,7 @@ int32_t b200rwkv_state_load(b200rwkv_engine* e, int32_t slot, const float* in) {
     API_END
 }
 
-int32_t b200rwkv_state_back(b200rwkv_engine* e, int32_t slot, float* out) {
+static int32_t rank_state_back(b200rwkv_engine* e, int32_t slot, float* out) {
     API_BEGIN(e)
     REQUIRE(e && out, B200RWKV_ERR_INVALID, "null argument");
     REQUIRE(slot >= 0 && slot < e->S, B200RWKV_ERR_STATE, "slot out of range");
@@ -1985,7 +2167,7 @@ static Snapshot snapshot_alloc(b200rwkv_engine* e, bool with_logits) {
     return sn;
 }
 
-int32_t b200rwkv_state_read(b200rwkv_engine* e, int32_t slot, uint64_t* snapshot_id) {
+static int32_t rank_state_read(b200rwkv_engine* e, int32_t slot, uint64_t* snapshot_id) {
     API_BEGIN(e)
     REQUIRE(e && snapshot_id, B200RWKV_ERR_INVALID, "null argument");
     REQUIRE(slot >= 0 && slot < e->S, B200RWKV_ERR_STATE, "slot out of range");
@@ -2014,7 +2196,7 @@ int32_t b200rwkv_state_read(b200rwkv_engine* e, int32_t slot, uint64_t* snapshot
     API_END
 }
 
-int32_t b200rwkv_state_write(b200rwkv_engine* e, int32_t slot, uint64_t snapshot_id) {
+static int32_t rank_state_write(b200rwkv_engine* e, int32_t slot, uint64_t snapshot_id) {
     API_BEGIN(e)
     REQUIRE(e, B200RWKV_ERR_INVALID, "null engine");
     REQUIRE(slot >= 0 && slot < e->S, B200RWKV_ERR_STATE, "slot out of range");
@@ -2034,7 +2216,7 @@ int32_t b200rwkv_state_write(b200rwkv_engine* e, int32_t slot, uint64_t snapshot
     API_END
 }
 
-int32_t b200rwkv_state_free(b200rwkv_engine* e, uint64_t snapshot_id) {
+static int32_t rank_state_free(b200rwkv_engine* e, uint64_t snapshot_id) {
     API_BEGIN(e)
     REQUIRE(e, B200RWKV_ERR_INVALID, "null engine");
     std::lock_guard<std::mutex> lk(e->mu);
@@ -2048,7 +2230,7 @@ int32_t b200rwkv_state_free(b200rwkv_engine* e, uint64_t snapshot_id) {
 }
 
 // ---- device-resident state cache: snapshots <-> host tensors, without passing through a slot ----
-int32_t b200rwkv_snapshot_back(b200rwkv_engine* e, uint64_t snapshot_id, float* state_out, float* logits_out) {
+static int32_t rank_snapshot_back(b200rwkv_engine* e, uint64_t snapshot_id, float* state_out, float* logits_out) {
     API_BEGIN(e)
     REQUIRE(e && (state_out || logits_out), B200RWKV_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(e->mu);
@@ -2068,7 +2250,7 @@ int32_t b200rwkv_snapshot_back(b200rwkv_engine* e, uint64_t snapshot_id, float* 
     API_END
 }
 
-int32_t b200rwkv_snapshot_load(b200rwkv_engine* e, const float* state_in, const float* logits_in, uint64_t* snapshot_id) {
+static int32_t rank_snapshot_load(b200rwkv_engine* e, const float* state_in, const float* logits_in, uint64_t* snapshot_id) {
     API_BEGIN(e)
     REQUIRE(e && state_in && snapshot_id, B200RWKV_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(e->mu);
@@ -2180,7 +2362,7 @@ static void build_decode_metas(b200rwkv_engine* e, int nslot, const int32_t* slo
     }
 }
 
-int32_t b200rwkv_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, int32_t warmup,
+static int32_t rank_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, int32_t warmup,
                               int32_t steps, int32_t flush_l2, float* ms_out, int64_t* launches_out, float* step_ms_out) {
     API_BEGIN(e)
     REQUIRE(e && slot && tokens && ms_out, B200RWKV_ERR_INVALID, "null argument");
@@ -2231,7 +2413,7 @@ int32_t b200rwkv_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_t* 
     API_END
 }
 
-int32_t b200rwkv_profile_step(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, float ms[4],
+static int32_t rank_profile_step(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, float ms[4],
                               int32_t launches[4], int64_t* gemm_weight_bytes) {
     API_BEGIN(e)
     REQUIRE(e && slot && tokens && ms && launches, B200RWKV_ERR_INVALID, "null argument");
@@ -2264,7 +2446,7 @@ int32_t b200rwkv_profile_step(b200rwkv_engine* e, int32_t nslot, const int32_t* 
 // exit]: with programmatic dependent launch a kernel is resident long before it may touch its inputs, so CUDA events around
 // launches (b200rwkv_profile_step) over-count; windows of consecutive launches cannot overlap (the wait returns only when the
 // previous grid has completed), so their sum is <= the step.  Averages over `reps` replays of a traced copy of the step graph.
-int32_t b200rwkv_profile_insitu(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, int32_t reps,
+static int32_t rank_profile_insitu(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, int32_t reps,
                                 int32_t cap, int32_t* n_out, int32_t* types, double* start_us, double* end_us, int64_t* bytes,
                                 double* step_us) {
     API_BEGIN(e)
@@ -2572,6 +2754,155 @@ int32_t b200rwkv_debug_prefetch(int32_t device, double mbytes, int32_t consumers
     CK(cudaFree(buf)); CK(cudaFree(fl));
     cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c);
     API_END
+}
+
+// ---- exported SPMD entries: one rank, or all ranks of an in-process tensor-parallel engine at once ----
+#define RANKS(e, call_r) ((e) && (e)->group ? (e)->group->spmd([&](int r_) -> int32_t { b200rwkv_engine* er = (e)->group->ranks[r_]; (void)er; return call_r; }) : [&]() -> int32_t { b200rwkv_engine* er = (e); const int r_ = 0; (void)r_; return call_r; }())
+
+int32_t b200rwkv_infer(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const int32_t* ntok, const uint32_t* tokens,
+                       const int32_t* option, float* logits_out, size_t logits_cap, int32_t* rows_out) {
+    return RANKS(e, rank_infer(er, nslot, slot, ntok, tokens, option, r_ == 0 ? logits_out : nullptr, r_ == 0 ? logits_cap : 0,
+                               r_ == 0 ? rows_out : nullptr));
+}
+int32_t b200rwkv_state_load(b200rwkv_engine* e, int32_t slot, const float* in) { return RANKS(e, rank_state_load(er, slot, in)); }
+
+// head-sharded state: every rank exports the WKV rows of its own heads (zeros elsewhere); the shift rows are replicated
+static void merge_state_columns(const b200rwkv_engine* lead, float* out, const float* part, int r) {
+    const int C = lead->C, N = lead->N, Cl = lead->Cl;
+    for (int l = 0; l < lead->L; ++l)
+        for (int row = 1; row <= N; ++row) {
+            const size_t o = ((size_t)l * (N + 2) + row) * C + (size_t)r * Cl;
+            memcpy(out + o, part + o, (size_t)Cl * 4);
+        }
+}
+int32_t b200rwkv_state_back(b200rwkv_engine* e, int32_t slot, float* out) {
+    if (!e || !e->group) return rank_state_back(e, slot, out);
+    const size_t n = (size_t)e->L * (e->N + 2) * e->C;
+    std::vector<std::vector<float>> part(e->group->ranks.size());
+    for (size_t r = 1; r < part.size(); ++r) part[r].resize(n);
+    const int32_t st = e->group->spmd([&](int r) { return rank_state_back(e->group->ranks[r], slot, r == 0 ? out : part[r].data()); });
+    if (st < 0 || !out) return st;
+    for (size_t r = 1; r < part.size(); ++r) merge_state_columns(e, out, part[r].data(), (int)r);
+    return st;
+}
+int32_t b200rwkv_state_read(b200rwkv_engine* e, int32_t slot, uint64_t* snapshot_id) {
+    if (!e || !e->group) return rank_state_read(e, slot, snapshot_id);
+    // every rank snapshots its shard; the ranks' id counters advance in lockstep, so the ids agree
+    std::vector<uint64_t> ids(e->group->ranks.size(), 0);
+    const int32_t st = e->group->spmd([&](int r) { return rank_state_read(e->group->ranks[r], slot, &ids[r]); });
+    if (st < 0) return st;
+    for (uint64_t id : ids)
+        if (id != ids[0]) { g_err = "internal: snapshot ids diverged across ranks"; return B200RWKV_ERR_STATE; }
+    if (snapshot_id) *snapshot_id = ids[0];
+    return st;
+}
+int32_t b200rwkv_state_write(b200rwkv_engine* e, int32_t slot, uint64_t id) { return RANKS(e, rank_state_write(er, slot, id)); }
+int32_t b200rwkv_state_free(b200rwkv_engine* e, uint64_t id) { return RANKS(e, rank_state_free(er, id)); }
+int32_t b200rwkv_snapshot_back(b200rwkv_engine* e, uint64_t id, float* state_out, float* logits_out) {
+    if (!e || !e->group) return rank_snapshot_back(e, id, state_out, logits_out);
+    const size_t n = (size_t)e->L * (e->N + 2) * e->C;
+    std::vector<std::vector<float>> part(e->group->ranks.size());
+    for (size_t r = 1; r < part.size(); ++r) part[r].resize(state_out ? n : 0);
+    const int32_t st = e->group->spmd([&](int r) {
+        if (r == 0) return rank_snapshot_back(e, id, state_out, logits_out);
+        return state_out ? rank_snapshot_back(e->group->ranks[r], id, part[r].data(), nullptr) : (int32_t)B200RWKV_OK;
+    });
+    if (st < 0 || !state_out) return st;
+    for (size_t r = 1; r < part.size(); ++r) merge_state_columns(e, state_out, part[r].data(), (int)r);
+    return st;
+}
+int32_t b200rwkv_snapshot_load(b200rwkv_engine* e, const float* state_in, const float* logits_in, uint64_t* snapshot_id) {
+    if (!e || !e->group) return rank_snapshot_load(e, state_in, logits_in, snapshot_id);
+    std::vector<uint64_t> ids(e->group->ranks.size(), 0);
+    const int32_t st = e->group->spmd([&](int r) { return rank_snapshot_load(e->group->ranks[r], state_in, r == 0 ? logits_in : nullptr, &ids[r]); });
+    if (st < 0) return st;
+    for (uint64_t id : ids)
+        if (id != ids[0]) { g_err = "internal: snapshot ids diverged across ranks"; return B200RWKV_ERR_STATE; }
+    if (snapshot_id) *snapshot_id = ids[0];
+    return st;
+}
+int32_t b200rwkv_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, int32_t warmup,
+                              int32_t steps, int32_t flush_l2, float* ms_out, int64_t* launches_out, float* step_ms_out) {
+    if (!e || !e->group) return rank_bench_decode(e, nslot, slot, tokens, warmup, steps, flush_l2, ms_out, launches_out, step_ms_out);
+    const size_t W = e->group->ranks.size();
+    std::vector<float> ms(W, 0.f);
+    std::vector<int64_t> ln(W, 0);
+    const int32_t st = e->group->spmd([&](int r) {
+        return rank_bench_decode(e->group->ranks[r], nslot, slot, tokens, warmup, steps, flush_l2, &ms[r], &ln[r], r == 0 ? step_ms_out : nullptr);
+    });
+    if (st < 0) return st;
+    if (ms_out) *ms_out = *std::max_element(ms.begin(), ms.end());        // a step is done when the slowest rank is
+    if (launches_out) *launches_out = ln[0];
+    return st;
+}
+int32_t b200rwkv_profile_step(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, float ms[4],
+                              int32_t launches[4], int64_t* gemm_weight_bytes) {
+    if (!e || !e->group) return rank_profile_step(e, nslot, slot, tokens, ms, launches, gemm_weight_bytes);
+    const size_t W = e->group->ranks.size();
+    std::vector<float> m4(4 * W);
+    std::vector<int32_t> l4(4 * W);
+    std::vector<int64_t> wb(W);
+    const int32_t st = e->group->spmd([&](int r) { return rank_profile_step(e->group->ranks[r], nslot, slot, tokens, &m4[4 * r], &l4[4 * r], &wb[r]); });
+    if (st < 0) return st;
+    for (int i = 0; i < 4; ++i) { ms[i] = m4[i]; launches[i] = l4[i]; }
+    if (gemm_weight_bytes) *gemm_weight_bytes = wb[0];
+    return st;
+}
+int32_t b200rwkv_profile_insitu(b200rwkv_engine* e, int32_t nslot, const int32_t* slot, const uint32_t* tokens, int32_t reps,
+                                int32_t cap, int32_t* n_out, int32_t* types, double* start_us, double* end_us, int64_t* bytes,
+                                double* step_us) {
+    if (!e || !e->group) return rank_profile_insitu(e, nslot, slot, tokens, reps, cap, n_out, types, start_us, end_us, bytes, step_us);
+    const size_t W = e->group->ranks.size();
+    std::vector<std::vector<int32_t>> ty(W, std::vector<int32_t>(cap));
+    std::vector<std::vector<double>> su(W, std::vector<double>(cap)), eu(W, std::vector<double>(cap));
+    std::vector<std::vector<int64_t>> by(W, std::vector<int64_t>(cap));
+    std::vector<int32_t> nn(W, 0);
+    std::vector<double> sus(W, 0.0);
+    const int32_t st = e->group->spmd([&](int r) {
+        if (r == 0) return rank_profile_insitu(e, nslot, slot, tokens, reps, cap, n_out, types, start_us, end_us, bytes, step_us);
+        return rank_profile_insitu(e->group->ranks[r], nslot, slot, tokens, reps, cap, &nn[r], ty[r].data(), su[r].data(), eu[r].data(), by[r].data(), &sus[r]);
+    });
+    return st;
+}
+#undef RANKS
+
+// Replaces `ModelBuilder...build_vN()` + `Bundle::new` + `TokioRuntime::new` (lib.rs:484-497) with everything the reference's
+// ReloadRequest carries for this path: devices (one engine object owning all tensor-parallel ranks), LoRA files
+// (lib.rs:466-485), precision (lib.rs:493).
+int32_t b200rwkv_create_ex(const uint8_t* st, size_t len, const b200rwkv_options* opt, b200rwkv_engine** out) {
+    if (!out || !opt) { g_err = "null argument"; return B200RWKV_ERR_INVALID; }
+    *out = nullptr;
+    if (opt->struct_bytes != sizeof(b200rwkv_options)) { g_err = "b200rwkv_options.struct_bytes does not match this library"; return B200RWKV_ERR_INVALID; }
+    const int world = opt->num_devices <= 0 ? 1 : opt->num_devices;
+    if (!(world == 1 || world == 2 || world == 4 || world == 8)) { g_err = "num_devices must be 1, 2, 4 or 8"; return B200RWKV_ERR_INVALID; }
+    if (opt->num_lora < 0 || opt->num_lora > B200RWKV_MAX_LORA) { g_err = "bad num_lora"; return B200RWKV_ERR_INVALID; }
+    std::vector<LoraArg> lora;
+    for (int i = 0; i < opt->num_lora; ++i) lora.push_back({opt->lora_st[i], opt->lora_len[i], opt->lora_alpha[i]});
+    const int dev0 = opt->num_devices <= 0 ? 0 : opt->devices[0];
+    if (world == 1) return create_rank(st, len, dev0, opt->max_batch, opt->token_chunk_size, opt->precision, 0, 1, lora, out);
+    for (int r = 0; r < world; ++r)
+        for (int q = 0; q < r; ++q)
+            if (opt->devices[r] == opt->devices[q]) { g_err = "devices must be distinct"; return B200RWKV_ERR_INVALID; }
+    // build all ranks concurrently (each uploads and re-tiles its own shard), then wire them
+    std::unique_ptr<Group> g(new Group());
+    g->ranks.assign(world, nullptr);
+    g->start(world);
+    const int32_t st_build = g->spmd([&](int r) {
+        return create_rank(st, len, opt->devices[r], opt->max_batch, opt->token_chunk_size, opt->precision, r, world, lora, &g->ranks[r]);
+    });
+    int32_t rc = st_build;
+    if (rc >= 0) rc = b200rwkv_tp_connect_local(g->ranks.data(), world);
+    if (rc < 0) {
+        const std::string msg = g_err;
+        g->shutdown();
+        for (auto* p : g->ranks) delete p;
+        g_err = msg;
+        return rc;
+    }
+    b200rwkv_engine* lead = g->ranks[0];
+    lead->group = std::move(g);
+    *out = lead;
+    return B200RWKV_OK;
 }
 
 const char* b200rwkv_last_error(b200rwkv_engine* e) { (void)e; return g_err.c_str(); }

@@ -112,6 +112,26 @@ __global__ void tp_barrier_kernel(const TpBar b) {
     tp_barrier(b, threadIdx.x);
 }
 
+// ---------------------------------------------------------------------------------------
+// LoRA blend at load (reference lib.rs:466-485: `ModelBuilder::lora(Lora { data, blend: LoraBlend::full(alpha) })`):
+//   W[o][i] <- f16( f32(W[o][i]) + alpha * sum_r B[o][r] * At[i][r] )
+// with the on-disk layout the reference's converter writes (assets/scripts/convert_safetensors.py:96-101,
+// crates/converter/src/main.rs:8-22): `<name>.lora.1` = lora_B [out, r], `<name>.lora.0` = lora_A transposed = [in, r].
+// One thread per element, f32 accumulation in rank order, one rounding.
+// ---------------------------------------------------------------------------------------
+__global__ void lora_blend_kernel(__half* __restrict__ W, const __half* __restrict__ B, const __half* __restrict__ At, int out, int in,
+                                  int r, float alpha) {
+    const size_t n = (size_t)out * in;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(e / in), i = (int)(e - (size_t)o * in);
+        const __half* b = B + (size_t)o * r;
+        const __half* a = At + (size_t)i * r;
+        float acc = 0.f;
+        for (int k = 0; k < r; ++k) acc = fmaf(__half2float(b[k]), __half2float(a[k]), acc);
+        W[e] = __float2half_rn(__half2float(W[e]) + alpha * acc);
+    }
+}
+
 __global__ void f16_to_f32_kernel(const __half* __restrict__ src, float* __restrict__ dst, size_t n, float scale, float bias) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         dst[i] = __half2float(src[i]) * scale + bias;

@@ -225,14 +225,36 @@ class Model:
     `TokioRuntime::new(bundle)`, lib.rs:484-497)."""
 
     def __init__(self, st: np.ndarray, max_batch: int = 8, token_chunk_size: int = 128, device: int = 0,
-                 precision: int = 0, rank: int = 0, world: int = 1, exact: bool = False):
+                 precision: int = 0, rank: int = 0, world: int = 1, exact: bool = False, devices=None, lora=None):
+        """devices: list of CUDA ordinals -> ONE engine object owning all tensor-parallel ranks (b200rwkv_create_ex);
+        lora: list of (st_bytes, alpha) blended at load (reference lib.rs:466-485);
+        rank / world: one process per GPU instead (b200rwkv_create_tp + tp.connect)."""
         if exact:
             precision = 1          # `Bundle::<f32>`: f32-exact activations (split hi + lo f16 operands)
         st = np.ascontiguousarray(st, dtype=np.uint8)
         h = C.c_void_p()
         L = capi.lib()
-        capi.check(L.b200rwkv_create_tp(capi.ptr(st), st.size, device, max_batch, token_chunk_size, precision,
-                                        rank, world, C.byref(h)))
+        if devices is not None or lora:
+            if world != 1:
+                raise capi.B200Error(capi.ERR_INVALID, "devices / lora go through b200rwkv_create_ex (in-process ranks)")
+            opt = capi.Options()
+            opt.struct_bytes = C.sizeof(capi.Options)
+            opt.max_batch, opt.token_chunk_size, opt.precision = max_batch, token_chunk_size, precision
+            devs = list(devices) if devices is not None else [device]
+            opt.num_devices = len(devs)
+            for i, d in enumerate(devs):
+                opt.devices[i] = int(d)
+            self._lora_keep = []
+            for i, (img, alpha) in enumerate(lora or []):
+                img = np.ascontiguousarray(img, dtype=np.uint8)
+                self._lora_keep.append(img)
+                opt.lora_st[i], opt.lora_len[i], opt.lora_alpha[i] = img.ctypes.data, img.size, float(alpha)
+            opt.num_lora = len(lora or [])
+            capi.check(L.b200rwkv_create_ex(capi.ptr(st), st.size, C.byref(opt), C.byref(h)))
+            self._lora_keep = []
+        else:
+            capi.check(L.b200rwkv_create_tp(capi.ptr(st), st.size, device, max_batch, token_chunk_size, precision,
+                                            rank, world, C.byref(h)))
         self._h = h
         self.max_batch, self.token_chunk_size = max_batch, token_chunk_size
         self.rank, self.world = rank, world

@@ -111,7 +111,11 @@ def tensor_spec(s: Shape) -> list[tuple[str, tuple[int, ...], float, float]]:
             add(a + "v1", (s.Dv, C), -0.5 * _sq(C), 0.5 * _sq(C))
             add(a + "v2", (C, s.Dv), -1.0 * _sq(s.Dv), 1.0 * _sq(s.Dv))
             add(a + "g1", (s.Dg, C), -1.0 * _sq(C), 1.0 * _sq(C))
-            add(a + "g2", (C, s.Dg), -2.0 * _sq(s.Dg), 2.0 * _sq(s.Dg))
+            # gate LoRA / output gains sized so that the synthetic model is as well conditioned as the RWKV-6 presets: with
+            # gain 2 / 0.5 here the random RWKV-7 stack is chaotic (two f32 implementations that differ only in summation
+            # order are 3e-3 apart after one token at 32 layers, f16 vs f32 operands 0.3: profiles/r02_findings.md), which
+            # says nothing about an engine; trained RWKV-7 checkpoints initialise both near zero.
+            add(a + "g2", (C, s.Dg), -1.0 * _sq(s.Dg), 1.0 * _sq(s.Dg))
             add(a + "k_k", (1, 1, C), 0.5, 1.2)
             add(a + "k_a", (1, 1, C), 0.0, 1.0)
             add(a + "r_k", (H, N), -0.3, 0.3)
@@ -119,7 +123,8 @@ def tensor_spec(s: Shape) -> list[tuple[str, tuple[int, ...], float, float]]:
             add(a + n + ".weight", (C, C), -_sq(C), _sq(C))
         if s.version != 7:
             add(a + "gate.weight", (C, C), -_sq(C), _sq(C))
-        add(a + "output.weight", (C, C), -0.5 * _sq(C), 0.5 * _sq(C))
+        og = 0.25 if s.version == 7 else 0.5
+        add(a + "output.weight", (C, C), -og * _sq(C), og * _sq(C))
         add(a + "ln_x.weight", (C,), 0.8, 1.2)
         add(a + "ln_x.bias", (C,), -0.05, 0.05)
         if s.time_state:
@@ -211,6 +216,38 @@ def make_st(shape: Shape | str, seed: int = 0, force_numpy: bool = False) -> np.
         view = buf[base + b:base + e].view(np.float16)
         fill(view, name_seed(name, seed), lo, hi, force_numpy)
     return buf
+
+
+def pack_st(tensors: dict[str, np.ndarray]) -> np.ndarray:
+    """safetensors image of a dict of arrays (F16 / F32), metadata {"format": "pt"}."""
+    header = {"__metadata__": {"format": "pt"}}
+    off, blobs = 0, []
+    for name, a in tensors.items():
+        a = np.ascontiguousarray(a)
+        dt = {np.dtype(np.float16): "F16", np.dtype(np.float32): "F32"}[a.dtype]
+        header[name] = {"dtype": dt, "shape": list(a.shape), "data_offsets": [off, off + a.nbytes]}
+        blobs.append(a.tobytes())
+        off += a.nbytes
+    hjson = json.dumps(header, separators=(",", ":")).encode("utf-8")
+    hjson += b" " * ((-len(hjson)) % 8)
+    return np.frombuffer(struct.pack("<Q", len(hjson)) + hjson + b"".join(blobs), dtype=np.uint8).copy()
+
+
+def make_lora_st(shape: Shape | str, rank: int = 8, seed: int = 1, targets=("att.key", "att.value", "att.output", "ffn.key", "ffn.value")) -> np.ndarray:
+    """Synthetic LoRA file in the layout the reference's converter writes (assets/scripts/convert_safetensors.py:96-101):
+    `<name>.lora.0` = lora_A transposed = [in, r], `<name>.lora.1` = lora_B = [out, r], float16, for every block and `head`."""
+    if isinstance(shape, str):
+        shape = PRESETS[shape]
+    dims = {n: shp for n, shp, _, _ in tensor_spec(shape)}
+    out = {}
+    names = [f"blocks.{l}.{t}" for l in range(shape.L) for t in targets if f"blocks.{l}.{t}.weight" in dims] + ["head"]
+    for base in names:
+        o, i = dims[base + ".weight"]
+        for idx, (rows, gain) in enumerate(((i, 1.0), (o, 1.0))):
+            a = np.empty(rows * rank, np.float16)
+            fill(a, name_seed(f"{base}.lora.{idx}", seed), -gain * _sq(rank) * 0.5, gain * _sq(rank) * 0.5, True)
+            out[f"{base}.lora.{idx}"] = a.reshape(rows, rank)
+    return pack_st(out)
 
 
 def num_params(shape: Shape | str) -> int:

@@ -75,6 +75,30 @@ int32_t b200rwkv_info_from_st(const uint8_t* st, size_t len, b200rwkv_info* out)
 int32_t b200rwkv_create(const uint8_t* st, size_t len, int32_t device, int32_t max_batch,
                         int32_t token_chunk_size, int32_t precision, b200rwkv_engine** out);
 
+/* Everything the reference's ReloadRequest carries for this path (crates/ai00-core/src/lib.rs:196-240, 484-497), one call:
+ *   - devices: `num_devices` in {1, 2, 4, 8} CUDA ordinals of this box.  With more than one, the returned handle is ONE engine
+ *     that owns every tensor-parallel rank (head / column parallel) and one worker thread per rank: every call
+ *     below is made once, by the same two tasks as before, and drives all GPUs -- the reference's single `Runtime` object
+ *     (run.rs:1230-1234).  State tensors are merged / scattered by head inside state_back / state_load.
+ *   - LoRA files blended into the projection matrices while they are uploaded (lib.rs:466-485, `LoraBlend::full(alpha)`):
+ *     `<name>.lora.1` [out, r] and `<name>.lora.0` [in, r] as the reference's converter writes them
+ *     (assets/scripts/convert_safetensors.py:96-101); W += alpha * lora.1 @ lora.0^T in f32, rounded once to f16.  Files with
+ *     anything but low-rank pairs on att.{receptance,key,value,gate,output} / ffn.{key,value,receptance} / head are
+ *     B200RWKV_ERR_UNSUPPORTED.  Images are borrowed during the call only.
+ * Set struct_bytes = sizeof(b200rwkv_options); zero the rest for defaults (device 0, no LoRA, fp16). */
+#define B200RWKV_MAX_LORA 4
+typedef struct {
+    uint32_t struct_bytes;
+    int32_t max_batch, token_chunk_size, precision;
+    int32_t num_devices;              /* 0 or 1: single GPU, devices[0] (0 if num_devices == 0) */
+    int32_t devices[8];
+    int32_t num_lora;
+    const uint8_t* lora_st[B200RWKV_MAX_LORA];
+    size_t lora_len[B200RWKV_MAX_LORA];
+    float lora_alpha[B200RWKV_MAX_LORA];
+} b200rwkv_options;
+int32_t b200rwkv_create_ex(const uint8_t* st, size_t len, const b200rwkv_options* opt, b200rwkv_engine** out);
+
 /* Tensor-parallel construction, one process per GPU (head / column parallel).
  * Every rank calls create_tp with the same model, then exchanges the opaque handle blobs
  * (b200rwkv_tp_export on each rank, all-gathered by the host over any side channel) and

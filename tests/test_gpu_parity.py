@@ -485,3 +485,31 @@ def test_device_resident_state_cache(models):
         m.sample_topk([1], top_k=3)                  # that snapshot carried no logits row
     snap.free(); snap2.free()
     assert m.state.cache_stats()["snapshots"] == n0
+
+
+def test_lora_blend_at_load():
+    """`ModelBuilder::lora(Lora { data, blend: LoraBlend::full(alpha) })` (reference lib.rs:466-485): the engine blends the
+    low-rank pairs into the projection matrices while uploading them; the oracle runs on weights blended by the CPU restatement."""
+    st = synth.make_st("small6", 0)
+    lora = synth.make_lora_st("small6", rank=8)
+    alpha = 0.75
+    base = O.parse_st(st)
+    orc = O.Oracle(O.blend_lora(base, O.parse_st(lora), alpha), "f16")
+    plain = O.Oracle(base, "f16")
+    m = runtime.Model(st, max_batch=2, token_chunk_size=32, lora=[(lora, alpha)])
+    try:
+        toks = [3, 9, 200, 41, 7]
+        m.state.load(m.state.init(), 0)
+        got = feed(m, 0, toks, full=True)
+        want, _ = orc.run(toks, orc.state_init(), full=True)
+        unblended, _ = plain.run(toks, plain.state_init(), full=True)
+        assert rel_err(got, want) <= REL_TOL and (got.argmax(1) == want.argmax(1)).all()
+        assert rel_err(unblended, want) > 20 * REL_TOL            # the LoRA really changes the model
+    finally:
+        m.close()
+    # anything but low-rank pairs on projection matrices is refused, not ignored
+    bad = synth.pack_st({"blocks.0.att.time_mix_w1.lora.0": np.zeros((512, 4), np.float16),
+                         "blocks.0.att.time_mix_w1.lora.1": np.zeros((160, 4), np.float16)})
+    with pytest.raises(capi.B200Error) as ei:
+        runtime.Model(st, max_batch=2, token_chunk_size=32, lora=[(bad, 1.0)])
+    assert ei.value.code == capi.ERR_UNSUPPORTED
