@@ -2491,6 +2491,8 @@ static int32_t rank_profile_insitu(b200rwkv_engine* e, int32_t nslot, const int3
     e->step_trace_bytes.resize(n, 0);
     for (int r = 0; r < reps + 1; ++r) {        // first replay is warm-up
         CK(cudaMemsetAsync(e->d_step_trace, 0, (size_t)n * row * 8, e->stream));
+        build_decode_metas(e, nslot, slot, tokens, 1, all);      // a fresh step sequence number: the folded rendezvous keys on it
+        CK(cudaMemcpyAsync(e->d_meta, all.data(), e->meta_ints * 4, cudaMemcpyHostToDevice, e->stream));
         CK(cudaGraphLaunch(ge, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         if (r == 0) continue;
