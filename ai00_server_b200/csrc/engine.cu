@@ -443,10 +443,18 @@ struct b200rwkv_engine {
     size_t gemm_ws_floats = 0;
 
     // step plumbing
+    static constexpr int META_RING = 4;
+    cudaEvent_t meta_ev[META_RING] = {nullptr, nullptr, nullptr, nullptr};
+    bool hidden_keep = false;          // b200rwkv_keep_hidden: accumulate the hidden rows of every token of an infer call
+    float* d_hidden_all = nullptr;
+    size_t hidden_cap_rows = 0;
+    int hidden_rows = 0;
     int *d_meta = nullptr, *h_meta = nullptr;
     int* d_meta_all = nullptr;
     size_t meta_ints = 0;
     std::map<int, cudaGraphExec_t> graphs;
+    std::map<int, long long> graph_launches;   // kernels per captured step graph
+    long long launch_total = 0;                // kernels launched by this engine's steps since creation
     long long launches_last_step = 0;
     int last_T = 0;
 
@@ -552,6 +560,8 @@ b200rwkv_engine::~b200rwkv_engine() {
     if (tk_dev) cudaFree(tk_dev);
     if (tk_host) cudaFreeHost(tk_host);
     if (step_done) cudaEventDestroy(step_done);
+    for (auto& ev : meta_ev) if (ev) cudaEventDestroy(ev);
+    if (d_hidden_all) cudaFree(d_hidden_all);
     if (stream) cudaStreamDestroy(stream);
     if (sm_stream) cudaStreamDestroy(sm_stream);
 }
@@ -839,8 +849,9 @@ void b200rwkv_engine::build(const StFile& st) {
     // ---- step metadata ----
     meta_ints = MetaView::ints(maxT, S);
     d_meta = (int*)dalloc(meta_ints * 4);
-    CK(cudaMallocHost(&h_meta, meta_ints * 4));
-    memset(h_meta, 0, meta_ints * 4);
+    CK(cudaMallocHost(&h_meta, meta_ints * 4 * META_RING));
+    memset(h_meta, 0, meta_ints * 4 * META_RING);
+    for (auto& ev : meta_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     MetaView mv{d_meta, maxT, S};
 
     // ---- temp upload buffer: largest tensor ----
@@ -1582,6 +1593,7 @@ void b200rwkv_engine::run_step(int MT, int MTR) {
         if (mega_step) launch_mega(stream);
         else enqueue_step(stream, MT, MTR, nullptr);
         enqueue_keep(stream, MTR);
+        launch_total += launches_last_step;
         return;
     }
     const int key = mega_step ? 0 : MT * 8 + MTR;
@@ -1603,8 +1615,10 @@ void b200rwkv_engine::run_step(int MT, int MTR) {
         CK(cudaGraphInstantiate(&ge, g, 0));
         CK(cudaGraphDestroy(g));
         it = graphs.emplace(key, ge).first;
+        graph_launches[key] = launches_last_step;
     }
     CK(cudaGraphLaunch(it->second, stream));
+    launch_total += graph_launches[key];         // kernels of THIS graph, not of whichever was captured last
 }
 
 // fills one step's metadata; returns T
@@ -1688,35 +1702,72 @@ void b200rwkv_engine::infer(int nslot, const int32_t* slot, const int32_t* ntok,
     const bool copy_logits = want_logits && logits_out != nullptr;
     // f32-activation mode runs every step decode-shaped (<= 16 tokens): the split-operand kernels are the 16-token ones
     const int step_cap = std::min(chunk, split_on ? 16 : maxT);
-    // cursor over entries
-    std::vector<size_t> base(nslot + 1, 0);
-    for (int i = 0; i < nslot; ++i) base[i + 1] = base[i] + (size_t)ntok[i];
-    int ei = 0;
-    int eoff = 0;
-    float* out = logits_out;
-    while (ei < nslot) {
-        std::vector<int> s_slots, s_counts, s_out;
+    // Step packing: every step shares its token budget evenly over the entries that still have tokens (web-rwkv shares the
+    // chunk "fairly across slots"; results do not depend on the cut).  Many slots with one token each keep
+    // the WKV kernels wide (one CTA per head and slot) where a single slot with 64 tokens would run them 40 CTAs wide.
+    std::vector<size_t> base(nslot + 1, 0), row_base(nslot + 1, 0);
+    std::vector<int> pos(nslot, 0), rows_done(nslot, 0);
+    for (int i = 0; i < nslot; ++i) {
+        base[i + 1] = base[i] + (size_t)ntok[i];
+        const int r = (option[i] == B200RWKV_OPTION_FULL) ? ntok[i] : ((option[i] == B200RWKV_OPTION_LAST && ntok[i] > 0) ? 1 : 0);
+        row_base[i + 1] = row_base[i] + (size_t)r;
+    }
+    if (hidden_keep && total_tok > hidden_cap_rows) {
+        if (d_hidden_all) { CK(cudaFree(d_hidden_all)); d_hidden_all = nullptr; hidden_cap_rows = 0; }
+        const size_t want = std::max<size_t>(total_tok, 256);
+        CK(cudaMalloc(&d_hidden_all, want * C * 4));
+        hidden_cap_rows = want;
+    }
+    hidden_rows = 0;
+    int step_no = 0;
+    for (;;) {
+        int n_active = 0;
+        for (int i = 0; i < nslot; ++i) n_active += (pos[i] < ntok[i]);
+        if (n_active == 0) break;
+        std::vector<int> s_entry, s_slots, s_counts, s_out;
         std::vector<const uint32_t*> s_toks;
+        const int quota = std::max(1, step_cap / n_active);
         int used = 0;
-        while (ei < nslot && used < step_cap) {
-            const int remain = ntok[ei] - eoff;
-            if (remain <= 0) { ++ei; eoff = 0; continue; }
-            const int take = std::min(remain, step_cap - used);
-            s_slots.push_back(slot[ei]);
+        for (int i = 0; i < nslot && used < step_cap; ++i) {
+            const int remain = ntok[i] - pos[i];
+            if (remain <= 0) continue;
+            const int take = std::min({remain, quota, step_cap - used});
+            s_entry.push_back(i);
             s_counts.push_back(take);
-            s_toks.push_back(tokens + base[ei] + eoff);
-            const bool finishes = (take == remain);
-            s_out.push_back(option[ei] == B200RWKV_OPTION_FULL ? 2 : ((finishes && option[ei] == B200RWKV_OPTION_LAST) ? 1 : 0));
             used += take;
-            eoff += take;
-            if (finishes) { ++ei; eoff = 0; }
         }
-        if (used == 0) break;
+        for (size_t j = 0; j < s_entry.size() && used < step_cap; ++j) {      // left-over budget, in entry order
+            const int i = s_entry[j];
+            const int extra = std::min(ntok[i] - pos[i] - s_counts[j], step_cap - used);
+            s_counts[j] += extra;
+            used += extra;
+        }
+        for (size_t j = 0; j < s_entry.size(); ++j) {
+            const int i = s_entry[j];
+            s_slots.push_back(slot[i]);
+            s_toks.push_back(tokens + base[i] + pos[i]);
+            const bool finishes = (pos[i] + s_counts[j] == ntok[i]);
+            s_out.push_back(option[i] == B200RWKV_OPTION_FULL ? 2 : ((finishes && option[i] == B200RWKV_OPTION_LAST) ? 1 : 0));
+        }
+        // pinned metadata ring: a buffer is rewritten only after the copy that read it has completed
+        const int mb = step_no % META_RING;
+        if (step_no >= META_RING) CK(cudaEventSynchronize(meta_ev[mb]));
+        int* hm = h_meta + (size_t)mb * meta_ints;
         int R = 0;
-        const int T = fill_meta(h_meta, s_slots, s_counts, s_toks, s_out, &R);
+        const int T = fill_meta(hm, s_slots, s_counts, s_toks, s_out, &R);
         last_T = T;
-        CK(cudaMemcpyAsync(d_meta, h_meta, meta_ints * 4, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(d_meta, hm, meta_ints * 4, cudaMemcpyHostToDevice, stream));
+        CK(cudaEventRecord(meta_ev[mb], stream));
         run_step(mt_bucket(T), R > 0 ? mt_bucket(R) : 0);
+        if (hidden_keep) {       // hidden rows of every token of this call (b200rwkv_last_hidden), in entry order
+            int t0 = 0;
+            for (size_t j = 0; j < s_entry.size(); ++j) {
+                const int i = s_entry[j];
+                CK(cudaMemcpyAsync(d_hidden_all + (base[i] + pos[i]) * (size_t)C, d_hidden + (size_t)t0 * C, (size_t)s_counts[j] * C * 4,
+                                   cudaMemcpyDeviceToDevice, stream));
+                t0 += s_counts[j];
+            }
+        }
         CK(cudaEventRecord(step_done, stream));
         if (R > 0) {
             std::lock_guard<std::mutex> lk(keep_mu);
@@ -1724,17 +1775,44 @@ void b200rwkv_engine::infer(int nslot, const int32_t* slot, const int32_t* ntok,
                 if (s_out[i] != 0) keep_valid[s_slots[i]] = 1;
         }
         if (R > 0 && copy_logits) {
-            if (world == 1) {
-                CK(cudaMemcpyAsync(out, d_logits, (size_t)R * V * 4, cudaMemcpyDeviceToHost, stream));
-            } else {
-                for (int q = 0; q < world; ++q)      // column block q of every row, straight from rank q's shard
-                    CK(cudaMemcpy2DAsync(out + (size_t)q * Vl, (size_t)V * 4, peer_base[q] + off_logits, (size_t)Vl * 4,
-                                         (size_t)Vl * 4, R, cudaMemcpyDeviceToHost, stream));
+            // rows of this step sit in entry order in d_logits; an entry's rows land at its own place of the entry-major
+            // output, runs that are contiguous on both sides go out as one copy
+            int r0 = 0;
+            size_t j = 0;
+            while (j < s_entry.size()) {
+                const int i = s_entry[j];
+                int nr = s_out[j] == 2 ? s_counts[j] : (s_out[j] == 1 ? 1 : 0);
+                if (nr == 0) { ++j; continue; }
+                const size_t dst = row_base[i] + (size_t)rows_done[i];
+                int run = nr;
+                rows_done[i] += nr;
+                size_t k = j + 1;
+                while (k < s_entry.size()) {
+                    const int i2 = s_entry[k];
+                    const int nr2 = s_out[k] == 2 ? s_counts[k] : (s_out[k] == 1 ? 1 : 0);
+                    if (nr2 == 0) { ++k; continue; }
+                    if (row_base[i2] + (size_t)rows_done[i2] != dst + (size_t)run) break;
+                    rows_done[i2] += nr2;
+                    run += nr2;
+                    ++k;
+                }
+                float* o = logits_out + dst * (size_t)V;
+                if (world == 1) {
+                    CK(cudaMemcpyAsync(o, d_logits + (size_t)r0 * V, (size_t)run * V * 4, cudaMemcpyDeviceToHost, stream));
+                } else {
+                    for (int q = 0; q < world; ++q)      // column block q of every row, straight from rank q's shard
+                        CK(cudaMemcpy2DAsync(o + (size_t)q * Vl, (size_t)V * 4, peer_base[q] + off_logits + (size_t)r0 * Vl * 4,
+                                             (size_t)Vl * 4, (size_t)Vl * 4, run, cudaMemcpyDeviceToHost, stream));
+                }
+                r0 += run;
+                j = k;
             }
-            out += (size_t)R * V;
-        }
-        CK(cudaStreamSynchronize(stream));
+        }      // (the next step's head projection is ordered after these copies by the stream)
+        for (size_t j = 0; j < s_entry.size(); ++j) pos[s_entry[j]] += s_counts[j];
+        ++step_no;
     }
+    CK(cudaStreamSynchronize(stream));
+    if (hidden_keep) hidden_rows = (int)total_tok;
 }
 
 // GPU sampling front half (sample.cuh).  Runs on the softmax stream under the softmax mutex: the reference samples from the
@@ -2375,6 +2453,7 @@ static int32_t rank_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_
     const int nsteps = warmup + steps;
     std::vector<int> all;
     build_decode_metas(e, nslot, slot, tokens, nsteps, all);
+    long long launches_before = 0;
     int* d_all = nullptr;
     CK(cudaMalloc(&d_all, all.size() * 4));
     CK(cudaMemcpy(d_all, all.data(), all.size() * 4, cudaMemcpyHostToDevice));
@@ -2394,6 +2473,7 @@ static int32_t rank_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_
         if (st == warmup) {
             CK(cudaStreamSynchronize(e->stream));
             CK(cudaEventRecord(ea, e->stream));
+            launches_before = e->launch_total;
         }
         if (flush) CK(cudaMemsetAsync(flush, st & 0xff, flush_bytes, e->stream));
         CK(cudaMemcpyAsync(e->d_meta, d_all + (size_t)st * e->meta_ints, e->meta_ints * 4, cudaMemcpyDeviceToDevice, e->stream));
@@ -2407,7 +2487,7 @@ static int32_t rank_bench_decode(b200rwkv_engine* e, int32_t nslot, const int32_
         CK(cudaEventElapsedTime(step_ms_out + i, i == 0 ? ea : marks[i - 1], marks[i]));
     }
     for (auto& m : marks) cudaEventDestroy(m);
-    if (launches_out) *launches_out = (int64_t)e->launches_last_step * steps;   // counted when the step was enqueued / captured
+    if (launches_out) *launches_out = (int64_t)(e->launch_total - launches_before);
     CK(cudaEventDestroy(ea));
     CK(cudaEventDestroy(eb));
     if (flush) CK(cudaFree(flush));
@@ -2530,20 +2610,40 @@ static int32_t rank_profile_insitu(b200rwkv_engine* e, int32_t nslot, const int3
     API_END
 }
 
+int32_t b200rwkv_launch_count(b200rwkv_engine* e, int64_t* total) {
+    API_BEGIN(e)
+    REQUIRE(e && total, B200RWKV_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(e->mu);
+    *total = (int64_t)e->launch_total;
+    API_END
+}
+
+int32_t b200rwkv_keep_hidden(b200rwkv_engine* e, int32_t enable) {
+    API_BEGIN(e)
+    REQUIRE(e, B200RWKV_ERR_INVALID, "null engine");
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->hidden_keep = enable != 0;
+    e->hidden_rows = 0;
+    API_END
+}
+
+// returns the number of rows written (negative status on error)
 int32_t b200rwkv_last_hidden(b200rwkv_engine* e, float* out, size_t cap) {
-    if (!e || !out) return B200RWKV_ERR_INVALID;
-    std::string* errp_ = &g_err;
-    try {
+    int32_t rows = 0;
+    const int32_t st = [&]() -> int32_t {
+        API_BEGIN(e)
+        REQUIRE(e && out, B200RWKV_ERR_INVALID, "null argument");
         std::lock_guard<std::mutex> lk(e->mu);
         CK(cudaSetDevice(e->dev));
-        const size_t n = (size_t)e->last_T * e->C;
+        CK(cudaStreamSynchronize(e->stream));
+        const bool all = e->hidden_keep && e->d_hidden_all;
+        rows = all ? e->hidden_rows : e->last_T;
+        const size_t n = (size_t)rows * e->C;
         REQUIRE(n <= cap, B200RWKV_ERR_INVALID, "hidden buffer too small");
-        CK(cudaMemcpy(out, e->d_hidden, n * 4, cudaMemcpyDeviceToHost));
-        return e->last_T;
-    } catch (const Error& ex) {
-        *errp_ = ex.what();
-        return ex.code;
-    }
+        if (n) CK(cudaMemcpy(out, all ? e->d_hidden_all : e->d_hidden, n * 4, cudaMemcpyDeviceToHost));
+        API_END
+    }();
+    return st < 0 ? st : rows;
 }
 
 // Debug aid for the parity tests: copy a named internal activation buffer of the most recent

@@ -348,9 +348,18 @@ class Model:
                                                    capi.ptr(bv), top_k, capi.ptr(ids), capi.ptr(probs)), self._h)
         return ids, probs
 
-    def last_hidden(self) -> np.ndarray:
+    def launch_count(self) -> int:
+        n = C.c_int64(0)
+        capi.check(capi.lib().b200rwkv_launch_count(self._h, C.byref(n)), self._h)
+        return n.value
+
+    def keep_hidden(self, enable: bool = True) -> None:
+        capi.check(capi.lib().b200rwkv_keep_hidden(self._h, int(enable)), self._h)
+
+    def last_hidden(self, max_rows: int = 64) -> np.ndarray:
+        """Residual stream after the last layer per token of the most recent infer call (all tokens after keep_hidden())."""
         Cc = self.info["num_emb"]
-        buf = np.empty((64, Cc), np.float32)
+        buf = np.empty((max_rows, Cc), np.float32)
         r = capi.lib().b200rwkv_last_hidden(self._h, capi.ptr(buf), buf.size)
         capi.check(r, self._h)
         return buf[:r]

@@ -155,6 +155,103 @@ def cpu_arm(weights, batch: int, steps: int, warmup: int, toks_bt: np.ndarray, b
     return batch * done / dt, dt / done * 1e3, rc.num_threads(), done
 
 
+def prefill_main(args):
+    """cfg 5 (BASELINE.json configs[4]): `seqs` prompts of `seq_len` tokens through the embeddings route's path -- prefill with
+    no logits, then State::back of every slot (run.rs:984-989 returns the backed state as the embedding).  A "step" is one
+    pass over all seqs x seq_len tokens."""
+    import torch
+    from ai00_server_b200 import capi, runtime, synth
+    from oracle import rwkv_numpy as O
+    preset = args.preset if args.preset != "v6-7b" or "--preset" in sys.argv else "v6-3b"
+    shape = synth.PRESETS[preset]
+    B, Tn = args.seqs, args.seq_len
+    steps, warm = max(1, min(args.steps, 4)), max(3, args.warmup if args.warmup < 8 else 3)
+    metric = f"prefill tokens/s {MODEL_NAMES.get(preset, preset)} fp16 {B}x{Tn}-token inputs (embeddings route)"
+    st = synth.make_st(shape, 0)
+    model = runtime.Model(st, max_batch=B, token_chunk_size=64, device=0)
+    slots = list(range(B))
+    rng = np.random.default_rng(1234)
+    toks = rng.integers(1, min(shape.V, 65530), size=(B, Tn), dtype=np.int64)
+    model.state.load(model.state.init(), 0)
+    zero_snap = model.state.read(0)
+
+    def reset():
+        for s_ in slots:
+            model.state.write(zero_snap, s_)
+
+    for _ in range(warm):                                   # untimed: short passes through the same kernels
+        reset()
+        model.infer_raw(slots, [16] * B, toks[:, :16].reshape(-1).tolist(), [capi.OPTION_NONE] * B)
+    flat = toks.reshape(-1).tolist()
+    sampler = ClockSampler(0)
+    sampler.start()
+    t_dev, t_e2e = [], []
+    state_buf = np.empty((B,) + model.state.init().shape, np.float32)
+    launches0 = model.launch_count()
+    for _ in range(steps):
+        reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.infer_raw(slots, [Tn] * B, flat, [capi.OPTION_NONE] * B)         # returns after the last step completed
+        t1 = time.perf_counter()
+        for s_ in slots:
+            state_buf[s_] = model.state.back(s_)
+        t2 = time.perf_counter()
+        t_dev.append(t1 - t0); t_e2e.append(t2 - t0)
+    clocks = sampler.stop()
+    launches = model.launch_count() - launches0
+    ntok = B * Tn
+    dt, de = float(np.mean(t_dev)), float(np.mean(t_e2e))
+    checksum = [float(state_buf.astype(np.float64).sum()), float(np.abs(state_buf).astype(np.float64).sum())]
+    # parity spot check + CPU baseline (outside the timed region): the first sequences' first tokens against the C oracle
+    w = O.parse_st(st)
+    from oracle import ref_c
+    if not os.path.exists(ref_c.LIB_PATH):
+        from ai00_server_b200 import build
+        build.build_oracle()
+    rc = ref_c.RefC(w, "f16")
+    rc.set_num_threads(host_threads())
+    nb, nt = min(B, 4), min(Tn, 24)
+    cst = rc.state_init(nb)
+    c0 = time.perf_counter()
+    for j in range(nt):
+        rc.decode_step(toks[:nb, j], cst)
+    cdt = time.perf_counter() - c0
+    reset()
+    model.infer_raw(slots[:nb], [nt] * nb, toks[:nb, :nt].reshape(-1).tolist(), [capi.OPTION_NONE] * nb)
+    errs = [float(np.abs(model.state.back(i) - cst[i]).max() / np.abs(cst[i]).max()) for i in range(nb)]
+    peaks, peak_src = read_peaks()
+    n_pass = -(-ntok // 64)
+    wbytes = 2 * (synth.num_params(shape) - shape.V * shape.C)              # every pass streams all weights but the embedding
+    pass_bytes = wbytes + 64 * 2 * shape.L * (shape.H * 64 * 64 + 2 * shape.C) * 4
+    flops = 2.0 * (synth.num_params(shape) - 2 * shape.V * shape.C) * ntok  # no head: the route needs no logits
+    line = {"metric": metric, "value": ntok / dt, "unit": "tokens/s", "n_gpus": 1, "steps": steps, "warmup": warm,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"{preset} prefill, {B} sequences x {Tn} tokens, no logits, final state of every sequence returned",
+                       "preset": preset, "seqs": B, "seq_len": Tn, "tokens_per_pass": 64,
+                       "l2": "inputs larger than L2 (5.9 GB of weights streamed per 64-token pass), no flush"},
+            "clocks": clocks,
+            "e2e": {"value": ntok / de, "unit": "tokens/s", "ms_per_step": de * 1e3, "h2d_bytes_per_step": int(ntok * 4 + n_pass * 1800),
+                    "d2h_bytes_per_step": int(state_buf.nbytes),
+                    "api": "b200rwkv_infer (host token ids, OPTION_NONE) + b200rwkv_state_back of every slot (the embedding, run.rs:984-989)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "gemm_kernel (64-token passes: every pass streams all projection weights)",
+                         "achieved": n_pass * pass_bytes / dt / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": n_pass * pass_bytes / dt / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json ({peak_src})", "passes": n_pass, "bytes_per_pass": int(pass_bytes),
+                         "tensor_tflops_achieved": flops / dt / 1e12, "tensor_tflops_peak_sustained": peaks.get("bf16_tflops_sustained"),
+                         "note": "this route is tensor-bound only with >= 256 tokens per weight pass; at 64 tokens per pass it is bound "
+                                 "by re-streaming the weights (DESIGN.md: chunked prefill is the next step)"},
+            "cpu_baseline": {"value": nb * nt / cdt, "unit": "tokens/s", "cores": rc.num_threads(), "kind": "port",
+                             "sample": f"first {nt} tokens of the first {nb} sequences, C/OpenMP oracle (token by token)"},
+            "state_checksum": {"sum": checksum[0], "abs_sum": checksum[1]},
+            "parity_check": {"what": f"final state of the first {nb} sequences after {nt} tokens vs the C oracle (f16 contract), max rel",
+                             "max_rel_err": max(errs)}}
+    print(json.dumps(line))
+    zero_snap.free()
+    model.close()
+
+
 def main():
     global PRESET, BATCH
     ap = argparse.ArgumentParser()
@@ -166,10 +263,16 @@ def main():
     ap.add_argument("--preset", default=PRESET, help="model shape: v6-7b (headline), v6-3b, v7-2b9, v6-1b6 (BASELINE.json configs)")
     ap.add_argument("--batch", type=int, default=BATCH, help="concurrent slots, one token per slot per step")
     ap.add_argument("--exact", action="store_true", help="precision 1: f32-exact activations (split hi+lo operands)")
+    ap.add_argument("--mode", default="decode", choices=["decode", "prefill"],
+                    help="prefill = BASELINE.json configs[4]: the embeddings route's workload (prompts in, final states out)")
+    ap.add_argument("--seqs", type=int, default=256)
+    ap.add_argument("--seq-len", type=int, default=512)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     PRESET, BATCH = args.preset, args.batch
     METRIC = metric_name(PRESET, BATCH)
+    if args.mode == "prefill":
+        return prefill_main(args)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

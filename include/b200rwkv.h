@@ -216,9 +216,14 @@ int32_t b200rwkv_profile_insitu(b200rwkv_engine*, int32_t nslot, const int32_t* 
                                 int32_t cap, int32_t* n_out, int32_t* types, double* start_us, double* end_us, int64_t* bytes,
                                 double* step_us);
 
-/* Optional copy of the residual stream after the last layer for every token of the most
- * recent infer call ([T, C] f32) — the hidden state the documented embeddings route returns
- * (reference docs/doc-api/openai.md:376-437).  Returns the number of rows written. */
+/* Kernels launched by this engine's forward steps since creation (graph replays counted by their kernel nodes). */
+int32_t b200rwkv_launch_count(b200rwkv_engine*, int64_t* total);
+
+/* The residual stream after the last layer, one [num_emb] f32 row per token -- the hidden state the documented embeddings
+ * route returns (reference docs/doc-api/openai.md:376-437).  After b200rwkv_keep_hidden(e, 1) every infer call records the
+ * rows of ALL its tokens (entry order, like the token array); without it only the rows of the call's last internal step
+ * (<= 64 tokens) are available.  b200rwkv_last_hidden returns the number of rows written (negative status on error). */
+int32_t b200rwkv_keep_hidden(b200rwkv_engine*, int32_t enable);
 int32_t b200rwkv_last_hidden(b200rwkv_engine*, float* out, size_t cap);
 
 /* Test aid: copy a named internal activation buffer of the most recent step to the host as f32

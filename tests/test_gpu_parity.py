@@ -513,3 +513,41 @@ def test_lora_blend_at_load():
     with pytest.raises(capi.B200Error) as ei:
         runtime.Model(st, max_batch=2, token_chunk_size=32, lora=[(bad, 1.0)])
     assert ei.value.code == capi.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("preset", ["tiny6", "tiny7"])
+def test_last_hidden_covers_every_token_of_the_call(models, preset):
+    """The embeddings route returns hidden states (reference docs/doc-api/openai.md:376-437): after keep_hidden() one infer
+    call leaves the residual stream after the last layer for ALL its tokens, in entry order, across internal steps."""
+    m, orc, _ = models(preset, chunk=32)
+    rng = np.random.default_rng(41)
+    runs = [rng.integers(1, 500, size=n).tolist() for n in (45, 3, 20)]          # 68 tokens: three internal steps
+    for s in range(3):
+        m.state.load(m.state.init(), s)
+    m.keep_hidden(True)
+    try:
+        m.infer_raw([0, 1, 2], [len(r) for r in runs], sum(runs, []), [capi.OPTION_NONE] * 3)
+        got = m.last_hidden(max_rows=128)
+    finally:
+        m.keep_hidden(False)
+    assert got.shape[0] == 68
+    off = 0
+    for r in runs:
+        want, _ = orc.hidden(r, orc.state_init())
+        assert rel_err(got[off:off + len(r)], want) <= REL_TOL
+        off += len(r)
+
+
+def test_full_rows_stay_in_entry_order_when_steps_interleave_slots(models):
+    """Steps share their token budget over the slots (round robin), so the rows of a Full entry are produced across several
+    steps interleaved with other entries; the output buffer is still entry-major (run.rs:730 splits it per slot)."""
+    m, orc, _ = models("tiny6", chunk=8)
+    rng = np.random.default_rng(43)
+    runs = [rng.integers(1, 500, size=n).tolist() for n in (11, 5, 9)]
+    for s in range(3):
+        m.state.load(m.state.init(), s)
+    rows = m.infer_raw([0, 1, 2], [len(r) for r in runs], sum(runs, []), [capi.OPTION_FULL, capi.OPTION_LAST, capi.OPTION_FULL])
+    assert [r.shape[0] for r in rows] == [11, 1, 9]
+    for s, r in enumerate(runs):
+        want, _ = orc.run(r, orc.state_init(), full=(s != 1))
+        assert rel_err(rows[s], want) <= REL_TOL and (rows[s].argmax(1) == np.atleast_2d(want).argmax(1)).all()
