@@ -76,6 +76,7 @@ SYMBOLS = [
     ("b200rwkv_bench_decode", C.c_int32, [_P, C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64), _P]),
     ("b200rwkv_profile_step", C.c_int32, [_P, C.c_int32, _P, _P, C.POINTER(C.c_float * 4), C.POINTER(C.c_int32 * 4), C.POINTER(C.c_int64)]),
     ("b200rwkv_profile_insitu", C.c_int32, [_P, C.c_int32, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(C.c_double)]),
+    ("b200rwkv_op_wkv", C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [_P] * 14),
     ("b200rwkv_launch_count", C.c_int32, [_P, C.POINTER(C.c_int64)]),
     ("b200rwkv_keep_hidden", C.c_int32, [_P, C.c_int32]),
     ("b200rwkv_last_hidden", C.c_int32, [_P, _P, C.c_size_t]),
@@ -122,3 +123,18 @@ def info_from_st(st: np.ndarray) -> dict:
     out = Info()
     check(lib().b200rwkv_info_from_st(ptr(st), st.size, C.byref(out)))
     return out.as_dict()
+
+
+def op_wkv(version: int, r, k, v, w, state, u=None, a=None, k_k=None, k_a=None, r_k=None, g=None, lnx_w=None, lnx_b=None, device: int = 0):
+    """One launch of the WKV kernel (b200rwkv_op_wkv).  r, k, v: [T, H, 64]; state [H, 64, 64] = M[value][key] (updated copy
+    returned).  Returns (out [T, H, 64] f32, state)."""
+    r = np.ascontiguousarray(r, np.float32)
+    T, H, _ = r.shape
+    f = lambda x: None if x is None else np.ascontiguousarray(x, np.float32)
+    k, v, w, u, a, k_k, k_a, r_k, g, lnx_w, lnx_b = map(f, (k, v, w, u, a, k_k, k_a, r_k, g, lnx_w, lnx_b))
+    st = np.array(state, np.float32, copy=True, order="C")
+    out = np.empty((T, H, 64), np.float32)
+    p = lambda x: None if x is None else ptr(x)
+    check(lib().b200rwkv_op_wkv(device, version, T, H, p(r), p(k), p(v), p(w), p(u), p(a), p(k_k), p(k_a), p(r_k), p(g), p(lnx_w),
+                                p(lnx_b), p(st), p(out)))
+    return out, st

@@ -2610,6 +2610,78 @@ static int32_t rank_profile_insitu(b200rwkv_engine* e, int32_t nslot, const int3
     API_END
 }
 
+// Operator-level entry for the parity tests: ONE launch of the WKV kernel (recurrence + GroupNorm + bonus + gate) on caller
+// supplied head vectors and state, no model around it.  This is how the committed fla fixtures (tests/golden/wkv6_fla.npz,
+// wkv7_fla.npz: independent pins of the recurrences) reach the CUDA kernels.
+int32_t b200rwkv_op_wkv(int32_t device, int32_t version, int32_t T, int32_t H, const float* r, const float* k, const float* v,
+                        const float* w, const float* u, const float* a, const float* k_k, const float* k_a, const float* r_k,
+                        const float* g, const float* lnx_w, const float* lnx_b, float* state, float* out) {
+    API_BEGIN((b200rwkv_engine*)nullptr)
+    REQUIRE(version == 5 || version == 6 || version == 7, B200RWKV_ERR_UNSUPPORTED, "version must be 5, 6 or 7");
+    REQUIRE(T >= 1 && T <= 64 && H >= 1 && H <= 1024 && r && k && v && w && state && out, B200RWKV_ERR_INVALID, "bad argument");
+    REQUIRE(version == 7 ? (a && k_k && k_a && r_k) : (u != nullptr), B200RWKV_ERR_INVALID, "missing per-version operand");
+    CK(cudaSetDevice(device));
+    const int Cc = H * 64;
+    const size_t TC = (size_t)T * Cc;
+    std::vector<DevTmp*> keep;
+    struct Guard { std::vector<DevTmp*>& v; ~Guard() { for (auto* p : v) delete p; } } guard{keep};
+    auto up = [&](const float* h, size_t n, float fill) -> float* {
+        keep.push_back(new DevTmp(n * 4));
+        float* d = (float*)keep.back()->p;
+        if (h) CK(cudaMemcpy(d, h, n * 4, cudaMemcpyHostToDevice));
+        else {
+            std::vector<float> tmp(n, fill);
+            CK(cudaMemcpy(d, tmp.data(), n * 4, cudaMemcpyHostToDevice));
+        }
+        return d;
+    };
+    const int maxT = 64, maxS = 1;
+    std::vector<int> meta(MetaView::ints(maxT, maxS), 0);
+    meta[0] = T; meta[1] = 1; meta[2] = 0;
+    for (int t = 0; t < T; ++t) {
+        meta[8 + maxT + t] = 0;                       // tok_slot
+        meta[8 + 2 * maxT + t] = t == 0 ? -1 : t - 1; // tok_prev
+        meta[8 + 3 * maxT + t] = t == T - 1;          // tok_last
+        meta[8 + 5 * maxT + t] = -1;                  // tok_outrow
+    }
+    meta[8 + 6 * maxT] = 0; meta[8 + 6 * maxT + maxS] = 0; meta[8 + 6 * maxT + 2 * maxS] = T;
+    keep.push_back(new DevTmp(meta.size() * 4));
+    int* d_meta = (int*)keep.back()->p;
+    CK(cudaMemcpy(d_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice));
+    WkvParams p;
+    memset(&p, 0, sizeof(p));
+    p.version = version; p.ld = Cc; p.meta = MetaView{d_meta, maxT, maxS}; p.H = H;
+    p.state = up(state, (size_t)H * 64 * 64, 0.f);
+    p.r = up(r, TC, 0.f); p.k = up(k, TC, 0.f); p.v = up(v, TC, 0.f); p.g = up(g, TC, 1.f);
+    if (version == 5) p.w_static = up(w, Cc, 0.f); else p.w = up(w, TC, 0.f);
+    p.lnx_w = up(lnx_w, Cc, 1.f); p.lnx_b = up(lnx_b, Cc, 0.f);
+    if (version != 7) p.u = up(u, Cc, 0.f);
+    else {
+        p.a = up(a, TC, 0.f); p.nu = up(nullptr, TC, 0.f); p.v_first = up(nullptr, TC, 0.f); p.layer0 = 1;
+        p.k_k = up(k_k, Cc, 0.f); p.k_a = up(k_a, Cc, 0.f); p.r_k = up(r_k, Cc, 0.f);
+    }
+    const int kq = rup(Cc, GEMM_BK) / 32;
+    const size_t halves = (size_t)(maxT / 16) * kq * 512;
+    keep.push_back(new DevTmp(halves * 2));
+    p.out = (__half*)keep.back()->p;
+    p.kq_tile = kq;
+    CK(cudaMemset(p.out, 0, halves * 2));
+    const size_t smem = wkv_smem_bytes(version, false, 0, maxT);
+    switch (version) {
+        case 5: wkv_kernel<5><<<dim3(H, 1), WKV_SA_THREADS, smem>>>(p, maxT); break;
+        case 6: wkv_kernel<6><<<dim3(H, 1), WKV_SA_THREADS, smem>>>(p, maxT); break;
+        default: wkv_kernel<7><<<dim3(H, 1), WKV_SA_THREADS, smem>>>(p, maxT); break;
+    }
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<__half> ho(halves);
+    CK(cudaMemcpy(ho.data(), p.out, halves * 2, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < T; ++t)
+        for (int c = 0; c < Cc; ++c) out[(size_t)t * Cc + c] = __half2float(ho[a16_index(t, c, kq)]);
+    CK(cudaMemcpy(state, p.state, (size_t)H * 64 * 64 * 4, cudaMemcpyDeviceToHost));
+    API_END
+}
+
 int32_t b200rwkv_launch_count(b200rwkv_engine* e, int64_t* total) {
     API_BEGIN(e)
     REQUIRE(e && total, B200RWKV_ERR_INVALID, "null argument");

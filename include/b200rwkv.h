@@ -216,6 +216,17 @@ int32_t b200rwkv_profile_insitu(b200rwkv_engine*, int32_t nslot, const int32_t* 
                                 int32_t cap, int32_t* n_out, int32_t* types, double* start_us, double* end_us, int64_t* bytes,
                                 double* step_us);
 
+/* Operator-level entry (parity tests): one launch of the WKV kernel -- recurrence + per-head GroupNorm (eps 64e-5) (+ v7
+ * bonus) * gate -- on caller-supplied head vectors, for one sequence of T <= 64 tokens with H heads of size 64; no model.
+ * r, k, v, g: [T, H*64] (g NULL = 1); w: decay in (0, 1), [T, H*64] (v5: static [H*64]); u: v5/v6 time_first [H*64];
+ * v7: a [T, H*64], k_k / k_a / r_k [H*64] (kk = normalize_head(k * k_k), k <- k * (1 + (a - 1) * k_a), value-residual off);
+ * lnx_w / lnx_b [H*64] (NULL = 1 / 0); state: in/out [H][64][64] in the device orientation M[value][key] (v5/v6: the
+ * transpose of S[key][value]); out: [T, H*64], the f16 values the kernel hands to the output projection.  The committed
+ * flash-linear-attention fixtures (tests/golden/wkv6_fla.npz, wkv7_fla.npz) are checked through this entry. */
+int32_t b200rwkv_op_wkv(int32_t device, int32_t version, int32_t T, int32_t H, const float* r, const float* k, const float* v,
+                        const float* w, const float* u, const float* a, const float* k_k, const float* k_a, const float* r_k,
+                        const float* g, const float* lnx_w, const float* lnx_b, float* state, float* out);
+
 /* Kernels launched by this engine's forward steps since creation (graph replays counted by their kernel nodes). */
 int32_t b200rwkv_launch_count(b200rwkv_engine*, int64_t* total);
 
