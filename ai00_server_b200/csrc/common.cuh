@@ -44,7 +44,7 @@ __device__ __forceinline__ __half f2h_sat(float v) {
     v = fminf(fmaxf(v, -65504.f), 65504.f);
     return __float2half_rn(v);
 }
-// Split operand (opt-in B200RWKV_SPLIT_ACT=1): a projection input v travels as two f16 numbers hi + lo = v
+// Split operand (precision 1 = f32 activations): a projection input v travels as two f16 numbers hi + lo = v
 // (to ~2^-22 relative); hi sits at token row t, lo at row t + 16 of the same A16 buffer (the second 16-token tile), the
 // projection multiplies both tiles and its epilogue adds the two accumulator tiles.
 __device__ __forceinline__ void split_h(const float v, __half& hi, __half& lo) {
@@ -117,7 +117,7 @@ struct SpinGuard {          // poll(): call once per spin iteration
         }
     }
 };
-enum WatchCode : unsigned { WD_MBAR = 1, WD_GRIDBAR = 2, WD_A_STARTED = 3, WD_A_WSEQ = 4 };
+enum WatchCode : unsigned { WD_MBAR = 1, WD_GRIDBAR = 2 };
 
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -270,44 +270,8 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// Programmatic dependent launch: everything before this call may overlap the tail of the
-// preceding kernel in the stream/graph (weights are immutable, so weight prefetch may).
-// ---------------------------------------------------------------------------------------
-// Tensor-parallel rendezvous folded into the consumer kernel (opt-in, B200RWKV_TP_FOLD=1; written at the end of round 1,
-// NOT yet run on hardware).  The default path launches a one-warp `tp_barrier_kernel` between a row-parallel projection and
-// the LN stage that sums all ranks' partials: ~5 us per rendezvous (launch, flag round trip over NVLink, dependent release),
-// 65 per step.  Folded: every CTA of the consumer calls tp_rendezvous() right after griddepcontrol.wait (its own rank's
-// producer is complete and flushed): CTA 0 tells every peer "rank r reached site k of step seq", every CTA waits until all
-// peers said the same.  The epoch is seq * nb + k + 1 with seq uploaded with the step metadata, so nothing on the device
-// has to count and a captured graph replays correctly; flags only grow; compared modulo 2^32 ((int)(flag - epoch) >= 0), so the counters may wrap.
-// ---------------------------------------------------------------------------------------
-struct TpFold {
-    unsigned* flags[8];     // flags[q]: rank q's flag array [8] (peer-mapped for q != rank); a region of its own
-    const int* seq;         // step sequence number (meta[4])
-    int rank, world;        // world <= 1: no-op
-    int k, nb;              // rendezvous site of this launch, sites per step
-};
-__device__ __forceinline__ void tp_rendezvous(const TpFold& f) {
-    if (f.world <= 1) return;
-    const unsigned e = (unsigned)(*f.seq) * (unsigned)f.nb + (unsigned)f.k + 1u;
-    if ((int)threadIdx.x < f.world) {
-        const int q = threadIdx.x;
-        if (blockIdx.x == 0 && blockIdx.y == 0) {
-            __threadfence_system();
-            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.flags[q] + f.rank), "r"(e) : "memory");
-        }
-        SpinGuard sg_;
-        for (;;) {
-            unsigned v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f.flags[f.rank] + q) : "memory");
-            if ((int)(v - e) >= 0) break;          // wrap-safe comparison of 32-bit epochs
-            sg_.poll(6u, (unsigned)q, e, v);
-        }
-        __threadfence_system();
-    }
-    __syncthreads();
-}
-
+// Programmatic dependent launch: everything before griddepcontrol.wait may overlap the tail of the preceding kernel in the
+// stream / graph (weights and step metadata are immutable while a step runs, so prefetching them may).
 // profiling aid: globaltimer stamp i of this launch's trace row (CTA 0, thread 0 only; `tr` is null in production)
 __device__ __forceinline__ void trace_stamp(unsigned long long* tr, const int i) {
     if (tr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
@@ -332,22 +296,14 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-// CTA-wide sync domain: stand-alone kernels sync the whole CTA; inside the persistent whole-step
-// kernel (mega.cuh) only the 256 consumer threads take part (the producer warp runs free).
-constexpr int CONSUMER_THREADS = 256;
-template <bool MEGA>
-__device__ __forceinline__ void cta_sync() {
-    if (MEGA) named_bar_sync(1, CONSUMER_THREADS);
-    else __syncthreads();
-}
 // block-wide sum over 256 threads; `red` is >= 8 floats of shared memory; result broadcast
-template <bool MEGA>
+constexpr int CONSUMER_THREADS = 256;
 __device__ __forceinline__ float block_sum(float v, float* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     v = warp_sum(v);
-    cta_sync<MEGA>();   // protect `red` from the previous use
+    __syncthreads();   // protect `red` from the previous use
     if (lane == 0) red[warp] = v;
-    cta_sync<MEGA>();
+    __syncthreads();
     float t = (lane < CONSUMER_THREADS / 32) ? red[lane] : 0.f;
     t = warp_sum(t);
     return t;

@@ -21,13 +21,13 @@
 #include <vector>
 
 #include "gemm.cuh"
-#include "lora.cuh"
 #include "pre6.cuh"
 #include "sample.cuh"
-#include "mega.cuh"
 #include "misc.cuh"
 #include "mix.cuh"
+#ifdef B200RWKV_DEBUG
 #include "streamtest.cuh"
+#endif
 #include "wkv.cuh"
 
 namespace b200 {
@@ -52,6 +52,17 @@ struct Error : std::runtime_error {
     } while (0)
 
 static thread_local std::string g_err;
+
+// Bring-up switches exist only in the debug build (-DB200RWKV_DEBUG, `python -m ai00_server_b200.build --debug` ->
+// libb200rwkv_dbg.so): the product library ignores the environment entirely.
+static inline const char* dbg_env(const char* name) {
+#ifdef B200RWKV_DEBUG
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 // watchdog record in mapped pinned host memory (see common.cuh)
 static unsigned* g_wd_host = nullptr;
@@ -355,7 +366,7 @@ struct A16Buf {
 struct Layer {
     LnMixParams ln1, ln2;
     std::vector<GemmLaunch> pre;    // launches between LN1 and WKV
-    int wd2_index = -1;             // v6: index in `pre` of the decay-LoRA stage-2 launch (folded into the WKV phase by the megakernel)
+    int wd2_index = -1;             // v6: index in `pre` of the decay-LoRA stage-2 launch (skipped when the WKV kernel evaluates it in place)
     WkvParams wkv;
     GemmLaunch o;
     std::vector<GemmLaunch> ffn;    // launches after LN2
@@ -405,9 +416,6 @@ struct b200rwkv_engine {
     int S = 0, chunk = 0, maxT = 64, precision = 0;
     int L = 0, C = 0, F = 0, V = 0, H = 0, N = 64, Cl = 0, Hl = 0, Fl = 0, Vl = 0;
     bool use_graph = true, use_pdl = true;
-    bool use_mega = false, mega_ok = false;   // whole-step kernel is opt-in (B200RWKV_MEGA=1): see DESIGN.md, measured slower in round 1
-    MegaParams mega;
-    std::vector<int> mega_phase_types;
     int split_att = 1, split_ffn = 1;
     // tensor parallel: one symmetric comm block per rank (partials, gate block, logits shard, flags)
     uint8_t* comm_base = nullptr;
@@ -416,7 +424,6 @@ struct b200rwkv_engine {
     bool connected = false;
     TpBar tpbar;
     unsigned* d_epoch = nullptr;
-    int skip_mask = 0;   // timing attribution only (B200RWKV_SKIP): 1 LN, 2 small GEMMs, 4 WKV, 8 big GEMMs, 16 head
     cudaStream_t stream = nullptr, sm_stream = nullptr;
     std::vector<void*> allocs;
     size_t weight_bytes_total = 0;
@@ -497,28 +504,14 @@ struct b200rwkv_engine {
     A16Buf a16_alloc(int K, int nmat = 1);
     GemmLaunch make_launch(std::vector<SegDesc>& segs, int force_grid = 0);
     int pick_split(int K, int tiles) const;
-    void build_mega(const StFile& st);
-    void build_mega_program();
     void finalize_tp();
-    bool mega_prepared = false, mega_lora_cc = false;
-    std::vector<WkvParams> mega_wkvs;
-    std::vector<SmallNParams> mega_smallns;
-    std::vector<SmallKParams> mega_smallks;
-    void launch_mega(cudaStream_t s);
-
     template <typename P, typename... X>
     void launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, size_t smem, const P& params, int cls, cudaStream_t s, Profiler* prof,
                   X... extra);
-    bool fold_wd2 = false, lora_cc = false;
-    int gemm_ring = 2;            // GemmCfg RING mode of the decode-shaped projection kernel
-    bool tp_fold = false;         // experimental: rendezvous folded into the LN kernels (common.cuh TpFold), B200RWKV_TP_FOLD=1
-    TpFold tpf{};                 // template of the per-launch descriptor (flags, seq, rank, world, nb)
-    unsigned step_seq = 0;        // step sequence number uploaded as meta[4] (wraps; the rendezvous compares modulo 2^32)
-    bool split_on = false;        // split operands in effect (split_act and the cluster LN kernels are available)
-    bool split_act = false;       // experimental split (hi + lo f16) projection operands for decode-shaped steps, B200RWKV_SPLIT_ACT=1
-    int wkv_stream = 0;           // experimental streaming WKV (wkv.cuh wkv_stream_kernel): slot groups per head, B200RWKV_WKV_STREAM=G
-    bool gemm_fin = false;        // experimental designated-finisher stream-K (gemm.cuh), B200RWKV_FINISHER=1
-    int sk_grid = 0;              // experimental: cap of the stream-K grid (B200RWKV_SK_GRID, e.g. 128 = 16 CTAs per GPC)
+    bool fold_wd2 = false;
+    unsigned step_seq = 0;        // step sequence number uploaded as meta[4]
+    bool split_on = false;        // precision 1: split (hi + lo f16) projection operands, every step decode-shaped
+    bool split_act = false;
     int prefetch_blocks = 16;     // L2 prefetch depth (32 KB blocks per CTA) into the next projection launch
     bool fused_pre = true, ln_cluster = true;     // decode-shaped cluster kernels of pre6.cuh
     bool fused_pre_ok = false, ln_cluster_ok = false;
@@ -718,7 +711,7 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
     g.grid = std::max(1, std::min(num_sms, std::max(tile, cdiv(blk, 4))));
     g.grid = std::min(g.grid, blk);
     if (force_grid > 0) g.grid = std::min(force_grid, blk);
-    else if (!getenv("B200RWKV_OLD_GRID")) {
+    else {
         // Whole tiles per CTA whenever that keeps >= 3/4 of the SMs streaming: no cross-CTA fix-up in the tail, and
         // (measured, profiles/r01_findings.md §7) grids of <= 16 CTAs per GPC finish together while 144-148 CTAs skew
         // by 25 % because the 18/20-SM GPCs share the same GPC bandwidth as the 16-SM ones.
@@ -726,14 +719,12 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
         else if (tile > num_sms)
             for (int cand = num_sms; cand * 4 >= num_sms * 3; --cand)
                 if (tile % cand == 0) { g.grid = cand; break; }
-    } else if (tile <= num_sms && tile * 10 >= num_sms * 9) g.grid = tile;
-    if (sk_grid > 0 && force_grid <= 0 && g.grid != tile && (tile <= num_sms || tile % g.grid != 0)) g.grid = std::min(g.grid, sk_grid);
+    }
     const int per_cta = std::max(1, blk / g.grid);
     g.p.max_contrib = cdiv(kbmax, per_cta) + 1;
     g.p.counters = (unsigned*)dalloc((size_t)tile * 4, true);
     g.p.nrows = d_meta;   // T by default
     g.p.w_lbo = GEMM_W_LBO; g.p.w_sbo = GEMM_W_SBO; g.p.a_lbo = GEMM_A_LBO; g.p.a_sbo = GEMM_A_SBO;
-    if (getenv("B200RWKV_UMMA_SWAP")) { std::swap(g.p.w_lbo, g.p.w_sbo); std::swap(g.p.a_lbo, g.p.a_sbo); }   // bring-up aid
     gemm_ws_floats = std::max(gemm_ws_floats, (size_t)tile * g.p.max_contrib * (size_t)maxT * GEMM_BN);
     weight_bytes_total += g.weight_bytes;
     return g;
@@ -780,13 +771,11 @@ void b200rwkv_engine::launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, siz
 }
 
 void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof, bool split) {
+    // RING 2 = one stage less than fits, so the small kernels around a projection can share its SMs (findings r1 §7)
     switch (MT) {
         case 1:
-            if (split) launch_k(gemm_kernel<2, 2, false, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<2, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
-            else if (gemm_ring == 1) launch_k(gemm_kernel<1, 1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
-            else if (gemm_fin) launch_k(gemm_kernel<1, 2, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
-            else if (gemm_ring == 2) launch_k(gemm_kernel<1, 2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
-            else launch_k(gemm_kernel<1>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            if (split) launch_k(gemm_kernel<2, 2, true>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<2, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            else launch_k(gemm_kernel<1, 2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             break;
         case 2: launch_k(gemm_kernel<2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<2>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
         default: launch_k(gemm_kernel<4>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<4>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
@@ -797,7 +786,7 @@ void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, P
 // into whole 128-wide blocks, gives every CTA whole tiles and puts the most SMs to work.  (Measured, round 2: with the
 // old cap of 4 the 3B channel-mix value projection ran on 40 CTAs, 22 us for 43 MB; 7 slices -> 140 CTAs.)
 int b200rwkv_engine::pick_split(int K, int tiles) const {
-    if (getenv("B200RWKV_NOSPLIT")) return 1;
+    if (dbg_env("B200RWKV_NOSPLIT")) return 1;
     const int kb = K / GEMM_BK;
     if (K % GEMM_BK != 0) return 1;
     int best = 1;
@@ -824,27 +813,14 @@ void b200rwkv_engine::build(const StFile& st) {
 
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&sm_stream, cudaStreamNonBlocking));
-    CK(cudaFuncSetAttribute(gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 1>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 2>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gemm_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 2>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(gemm_kernel<2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 2>::SMEM_BYTES));
-    CK(cudaFuncSetAttribute(wkv_stream_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    CK(cudaFuncSetAttribute(wkv_stream_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    if (const char* v = getenv("B200RWKV_GEMM_HALF")) gemm_ring = atoi(v) != 0 ? 1 : 0;
-    if (const char* v = getenv("B200RWKV_GEMM_RING")) gemm_ring = atoi(v);
-    if (const char* v = getenv("B200RWKV_PREFETCH_BLOCKS")) prefetch_blocks = std::max(0, atoi(v));
-    if (const char* v = getenv("B200RWKV_FINISHER")) gemm_fin = atoi(v) != 0;
-    if (const char* v = getenv("B200RWKV_WKV_STREAM")) wkv_stream = std::max(0, atoi(v));
-    if (const char* v = getenv("B200RWKV_SPLIT_ACT")) split_act = atoi(v) != 0 && world == 1;     // single GPU for now
-    if (precision == 1) split_act = true;         // f32-activation mode (web-rwkv `Bundle::<f32>`): no activation is rounded to f16
-    if (const char* v = getenv("B200RWKV_TP_FOLD")) tp_fold = atoi(v) != 0;
-    if (const char* v = getenv("B200RWKV_SK_GRID")) sk_grid = std::max(0, atoi(v));
-    if (const char* v = getenv("B200RWKV_LORA_CC")) lora_cc = atoi(v) != 0;
-    if (const char* v = getenv("B200RWKV_FUSED_PRE")) fused_pre = atoi(v) != 0;
-    if (const char* v = getenv("B200RWKV_LN_CLUSTER")) ln_cluster = atoi(v) != 0;
+    CK(cudaFuncSetAttribute(gemm_kernel<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 2>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<4>::SMEM_BYTES));
+    if (precision == 1) split_act = true;         // f32-activation mode (web-rwkv `Bundle::<f32>`): no activation is rounded to f16
+    if (const char* v = dbg_env("B200RWKV_PREFETCH_BLOCKS")) prefetch_blocks = std::max(0, atoi(v));
+    if (const char* v = dbg_env("B200RWKV_FUSED_PRE")) fused_pre = atoi(v) != 0;
+    if (const char* v = dbg_env("B200RWKV_LN_CLUSTER")) ln_cluster = atoi(v) != 0;
 
     // ---- step metadata ----
     meta_ints = MetaView::ints(maxT, S);
@@ -886,12 +862,12 @@ void b200rwkv_engine::build(const StFile& st) {
         d_logits = (float*)(comm_base + off_logits);
         d_epoch = (unsigned*)dalloc(16, true);
         pre_gbar = (unsigned*)dalloc(256, true);
-        if (getenv("B200RWKV_STEP_TRACE")) {
+        if (dbg_env("B200RWKV_STEP_TRACE")) {
             d_step_trace = (unsigned long long*)dalloc((size_t)STEP_TRACE_MAX * STEP_TRACE_ROW * 8, true);
             trace_capture = true;
         }
         ln_cluster_ok = ln_cluster && C % (4 * PRE_CLUSTER) == 0 && C / (4 * PRE_CLUSTER) <= PRE_THREADS;
-        split_on = split_act && ln_cluster_ok && !use_mega && !lora_cc;
+        split_on = split_act && ln_cluster_ok;
         REQUIRE(precision != 1 || split_on, B200RWKV_ERR_UNSUPPORTED, "precision 1 needs num_emb to be a multiple of 32 and <= 8192");
     }
     const int S_att = pick_split(Cl, cdiv(C, GEMM_BN)), S_ffn = pick_split(Fl, cdiv(C, GEMM_BN));
@@ -1059,7 +1035,7 @@ void b200rwkv_engine::build(const StFile& st) {
                 ly.wd2_index = (int)ly.pre.size();
                 ly.pre.push_back(make_launch(sv));
             }
-            if (Dd <= 128 && Dd % 8 == 0 && !getenv("B200RWKV_NOFOLD")) {
+            if (Dd <= 128 && Dd % 8 == 0 && !dbg_env("B200RWKV_NOFOLD")) {
                 // k-major copy of this rank's time_decay_w2 rows, one contiguous [Dd][64] slice per head: the WKV
                 // kernels evaluate the decay LoRA stage 2 themselves (one launch / phase less per layer)
                 const StTensor& t = st.get(a + "time_decay_w2");
@@ -1189,7 +1165,7 @@ void b200rwkv_engine::build(const StFile& st) {
             std::vector<SegDesc> sv;
             sv.push_back(a16_seg(Fk, f0, Fl, 0, C, a_x[0], a_kk, ACT_RELU2, nullptr));
             sv.push_back(f32_seg(st.get(f + "receptance.weight"), c0, Cl, 0, C, a_x[1], f_rr, Cl, ACT_SIGMOID, nullptr));
-            ly.ffn.push_back(make_launch(sv, getenv("B200RWKV_KR_GRID") ? atoi(getenv("B200RWKV_KR_GRID")) : 0));
+            ly.ffn.push_back(make_launch(sv));
         }
         {
             std::vector<SegDesc> sv;
@@ -1227,7 +1203,6 @@ void b200rwkv_engine::build(const StFile& st) {
     }
     head.p.ws = gemm_ws;
 
-    build_mega(st);
     if (world == 1) {
         peer_base[0] = comm_base;
         finalize_tp();
@@ -1265,158 +1240,12 @@ void b200rwkv_engine::finalize_tp() {
     }
     lnout.n_parts = parts_of(off_part_ffn, split_ffn, lnout.parts);
     if (ver != 7) { lnout.n_gate = world; lnout.gate_cl = Cl; gates_of(lnout.gates); }
-    memset(&tpf, 0, sizeof(tpf));
-    for (int q = 0; q < world; ++q) tpf.flags[q] = (unsigned*)(peer_base[q] + off_flags + 64);     // own 32 bytes of the flag area
-    tpf.seq = d_meta + 4;
-    tpf.rank = rank;
-    tpf.world = (tp_fold && world > 1) ? world : 0;
-    tpf.nb = 2 * L;
     memset(&tpbar, 0, sizeof(tpbar));
     for (int q = 0; q < world; ++q) tpbar.flags[q] = (unsigned*)(peer_base[q] + off_flags);
     tpbar.epoch = d_epoch;
     tpbar.rank = rank;
     tpbar.world = world;
-    build_mega_program();
     connected = true;
-}
-
-// -----------------------------------------------------------------------------------------
-// whole-step persistent kernel: device-side phase program over the same parameter blocks
-// -----------------------------------------------------------------------------------------
-// Part 1 (needs the model image): weight-side extras of the whole-step kernel.
-void b200rwkv_engine::build_mega(const StFile& st) {
-    mega_ok = false;
-    mega_prepared = false;
-    const int ver = info.version;
-    const int Dd = info.time_decay_adapter;
-    if (!use_mega && !lora_cc) return;
-    if (ver == 6 && (Dd > MEGA_MAX_DD || Dd % 8 != 0)) return;
-    if (C > MEGA_MAX_C) return;
-    mega_lora_cc = (ver == 6) && lora_cc && info.time_mix_adapter % 8 == 0 && info.time_mix_adapter <= 512 / 1 &&
-                   5 * info.time_mix_adapter <= num_sms * LORA_MAX_ROWS_PER_CTA;
-    auto upload_raw = [&](const StTensor& t) {
-        __half* d = (__half*)dalloc(t.nbytes, false);
-        CK(cudaMemcpy(d, t.data, t.nbytes, cudaMemcpyHostToDevice));
-        return d;
-    };
-    mega_wkvs.clear(); mega_smallns.clear(); mega_smallks.clear();
-    for (int l = 0; l < L; ++l) {
-        Layer& ly = layers[l];
-        WkvParams w = ly.wkv;
-        if (ver == 6 && !w.wd2t) return;      // decay LoRA not folded: this path needs it
-        mega_wkvs.push_back(w);
-        if (mega_lora_cc) {
-            // ddlerp LoRA on CUDA cores: no cross-CTA reduction (lora.cuh)
-            const int Dm = info.time_mix_adapter;
-            SmallNParams sn;
-            memset(&sn, 0, sizeof(sn));
-            sn.W = upload_raw(st.get("blocks." + std::to_string(l) + ".att.time_mix_w1"));
-            sn.N = 5 * Dm; sn.K = C;
-            sn.A = a_x[5].p; sn.a_kq = a_x[5].kq;
-            sn.out = a_lora[0].p; sn.grp = Dm; sn.grp_stride = (int)a_lora[0].halves_per_matrix; sn.out_kq = a_lora[0].kq;
-            sn.act = ACT_TANH; sn.nrows = d_meta;
-            mega_smallns.push_back(sn);
-            const __half* w2 = upload_raw(st.get("blocks." + std::to_string(l) + ".att.time_mix_w2"));
-            SmallKParams sk;
-            memset(&sk, 0, sizeof(sk));
-            sk.nseg = 5; sk.nrows = d_meta;
-            for (int j = 0; j < 5; ++j) {
-                const GemmSeg& gs_ = ly.pre[1].p.seg[j];
-                SmallKSeg& q = sk.seg[j];
-                q.W = w2 + (size_t)j * C * Dm; q.N = C; q.K = Dm;
-                q.A = a_lora[0].p + (size_t)j * a_lora[0].halves_per_matrix; q.a_kq = a_lora[0].kq;
-                q.out_mode = OUT_LERP_A16; q.act = ACT_NONE; q.bias = nullptr;
-                q.out = gs_.out; q.ldo = gs_.ldo; q.aux0 = gs_.aux0; q.aux1 = gs_.aux1; q.aux2 = gs_.aux2; q.ld_aux = gs_.ld_aux;
-            }
-            mega_smallks.push_back(sk);
-        }
-    }
-    mega_prepared = true;
-}
-
-// Part 2 (after the tensor-parallel wiring): the device-side phase program.
-void b200rwkv_engine::build_mega_program() {
-    mega_ok = false;
-    if (!mega_prepared || !use_mega) return;
-    const int ver = info.version;
-    std::vector<Phase> phases;
-    std::vector<LnMixParams> lns;
-    std::vector<GemmLaunchDev> gemms;
-    auto add_gemm = [&](const GemmLaunch& g) {
-        GemmLaunchDev d;
-        memset(&d, 0, sizeof(d));
-        d.p = g.p;
-        d.ncta = g.grid;
-        phases.push_back({PH_GEMM, (int)gemms.size()});
-        gemms.push_back(d);
-    };
-    phases.push_back({PH_EMBED, 0});
-    for (int l = 0; l < L; ++l) {
-        Layer& ly = layers[l];
-        phases.push_back({PH_LN, (int)lns.size()});
-        lns.push_back(ly.ln1);
-        for (int i = 0; i < (int)ly.pre.size(); ++i) {
-            if (i == ly.wd2_index) continue;
-            if (mega_lora_cc && i == 0) { phases.push_back({PH_SMALLN, l}); continue; }
-            if (mega_lora_cc && i == 1) { phases.push_back({PH_SMALLK, l}); continue; }
-            add_gemm(ly.pre[i]);
-        }
-        phases.push_back({PH_WKV, l});
-        add_gemm(ly.o);
-        if (world > 1) phases.push_back({PH_TPBAR, 0});
-        phases.push_back({PH_LN, (int)lns.size()});
-        lns.push_back(ly.ln2);
-        for (auto& g : ly.ffn) add_gemm(g);
-        if (world > 1) phases.push_back({PH_TPBAR, 0});
-    }
-    phases.push_back({PH_LNOUT, 0});
-    add_gemm(head);
-    if (world > 1) phases.push_back({PH_TPBAR, 0});     // logits shards complete on every rank
-
-    auto up = [&](const void* src, size_t bytes) {
-        void* d = dalloc(bytes, false);
-        CK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
-        return d;
-    };
-    memset(&mega, 0, sizeof(mega));
-    mega.phases = (const Phase*)up(phases.data(), phases.size() * sizeof(Phase));
-    mega.nphase = (int)phases.size();
-    mega.version = ver;
-    mega.embed = (const EmbedParams*)up(&embed, sizeof(embed));
-    mega.ln = (const LnMixParams*)up(lns.data(), lns.size() * sizeof(LnMixParams));
-    mega.gemm = (const GemmLaunchDev*)up(gemms.data(), gemms.size() * sizeof(GemmLaunchDev));
-    mega.wkv = (const WkvParams*)up(mega_wkvs.data(), mega_wkvs.size() * sizeof(WkvParams));
-    mega.lnout = (const LnOutParams*)up(&lnout, sizeof(lnout));
-    if (!mega_smallns.empty()) mega.smalln = (const SmallNParams*)up(mega_smallns.data(), mega_smallns.size() * sizeof(SmallNParams));
-    if (!mega_smallks.empty()) mega.smallk = (const SmallKParams*)up(mega_smallks.data(), mega_smallks.size() * sizeof(SmallKParams));
-    mega.tp = tpbar;
-    mega.gbar = (unsigned*)dalloc(16, true);
-    mega.meta = MetaView{d_meta, maxT, S};
-    if (getenv("B200RWKV_TRACE")) mega.trace = (unsigned long long*)dalloc((size_t)4 * phases.size() * 12 * 8, true);
-    mega_phase_types.clear();
-    for (auto& ph : phases) mega_phase_types.push_back(ph.type);
-    void (*kern)(MegaParams) = (ver == 6) ? mega_step_kernel<6> : (ver == 7 ? mega_step_kernel<7> : mega_step_kernel<5>);
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_SMEM_BYTES));
-    int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, MEGA_THREADS, MEGA_SMEM_BYTES));
-    mega_ok = nb >= 1;
-}
-
-void b200rwkv_engine::launch_mega(cudaStream_t s) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(num_sms);
-    cfg.blockDim = dim3(MEGA_THREADS);
-    cfg.dynamicSmemBytes = MEGA_SMEM_BYTES;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    void (*kern)(MegaParams) = (info.version == 6) ? mega_step_kernel<6> : (info.version == 7 ? mega_step_kernel<7> : mega_step_kernel<5>);
-    CK(cudaLaunchKernelEx(&cfg, kern, mega));
-    launches_last_step = 1;
 }
 
 // -----------------------------------------------------------------------------------------
@@ -1425,26 +1254,22 @@ void b200rwkv_engine::launch_mega(cudaStream_t s) {
 void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* prof) {
     launches_last_step = 0;
     const int rows = MT * 16;
-    const int sk = skip_mask;
-    auto big = [](const GemmLaunch& g) { return g.weight_bytes >= (8u << 20); };
-    auto gemm_skipped = [&](const GemmLaunch& g) { return big(g) ? (sk & 8) != 0 : (sk & 2) != 0; };
     auto pre_skipped = [&](const Layer& ly, int gi) {
-        if (fold_wd2 && gi == ly.wd2_index) return true;
-        return fused_pre_ok && MT == 1 && ly.w1_raw && gi < 2;
+        if (fold_wd2 && gi == ly.wd2_index) return true;                 // the WKV kernel evaluates the decay LoRA stage 2
+        return fused_pre_ok && MT == 1 && ly.w1_raw && gi < 2;           // the front-half kernel holds both ddlerp LoRA stages
     };
     // projection launches of this step in stream order: each one prefetches the head of the next into L2 (the last one
     // wraps around to the first launch of the next step)
     std::vector<const GemmLaunch*> seq;
-    if (prefetch_blocks > 0 && !(lora_cc && MT == 1)) {
+    if (prefetch_blocks > 0) {
         for (int l = 0; l < L; ++l) {
             const Layer& ly = layers[l];
             for (int gi = 0; gi < (int)ly.pre.size(); ++gi)
-                if (!pre_skipped(ly, gi) && !gemm_skipped(ly.pre[gi])) seq.push_back(&ly.pre[gi]);
-            if (!gemm_skipped(ly.o)) seq.push_back(&ly.o);
-            for (auto& g : ly.ffn)
-                if (!gemm_skipped(g)) seq.push_back(&g);
+                if (!pre_skipped(ly, gi)) seq.push_back(&ly.pre[gi]);
+            seq.push_back(&ly.o);
+            for (auto& g : ly.ffn) seq.push_back(&g);
         }
-        if (MTR > 0 && !(sk & 16)) seq.push_back(&head);
+        if (MTR > 0) seq.push_back(&head);
     }
     size_t seq_pos = 0;
     auto launch_gemm_chained = [&](const GemmLaunch& g, int mt) {
@@ -1465,26 +1290,17 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
         }
         launch_gemm(g2, mt, s, prof, split_on && MT == 1);      // split operands only when the whole step is decode-shaped
     };
-    auto gemm = [&](const GemmLaunch& g) {
-        if (gemm_skipped(g)) return;
-        launch_gemm_chained(g, MT);
-    };
-    if (!(sk & 1)) launch_k(embed_ln0_kernel, dim3(rows), dim3(LN_THREADS), 0, embed, KC_LN, s, prof);
-    const bool fold = tpf.world > 1;          // rendezvous inside the consumer kernels instead of tp_barrier_kernel launches
-    auto site = [&](int k) { TpFold f = tpf; f.k = k; if (k < 0) f.world = 0; return f; };
-    auto launch_ln = [&](const LnMixParams& lp0, int k) {
-        if (sk & 1) return;
+    auto gemm = [&](const GemmLaunch& g) { launch_gemm_chained(g, MT); };
+    launch_k(embed_ln0_kernel, dim3(rows), dim3(LN_THREADS), 0, embed, KC_LN, s, prof);
+    auto launch_ln = [&](const LnMixParams& lp0) {
         LnMixParams lp = lp0;
         lp.trace = tr_next(0);
-        lp.tp = site(fold ? k : -1);
         if (ln_cluster_ok && MT == 1) {
             launch_cluster = PRE_CLUSTER;
-            if (lp.tp.world > 1) launch_k(ln_mix_cluster_kernel<true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
-            else if (split_on) launch_k(ln_mix_cluster_kernel<false, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
+            if (split_on) launch_k(ln_mix_cluster_kernel<true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
             else launch_k(ln_mix_cluster_kernel<false>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
         } else {
-            if (lp.tp.world > 1) launch_k(ln_mix_kernel<true>, dim3(rows), dim3(LN_THREADS), 0, lp, KC_LN, s, prof);
-            else launch_k(ln_mix_kernel<false>, dim3(rows), dim3(LN_THREADS), 0, lp, KC_LN, s, prof);
+            launch_k(ln_mix_kernel, dim3(rows), dim3(LN_THREADS), 0, lp, KC_LN, s, prof);
         }
     };
     const int wkv_slots = std::min(S, rows);
@@ -1493,83 +1309,54 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
         const bool fused = fused_pre_ok && MT == 1 && ly.w1_raw;
         if (fused) {
             // LN1 + token shift + ddlerp LoRA (W1, tanh, W2, lerps) in one launch
-            if (!(sk & 1)) {
-                Pre6Params q;
-                memset(&q, 0, sizeof(q));
-                q.ln = ly.ln1;
-                q.ln.trace = tr_next(6);
-                q.ln.tp = site((fold && l > 0) ? 2 * l - 1 : -1);
-                q.W1 = ly.w1_raw; q.W2 = ly.w2_raw;
-                for (int j = 0; j < 5; ++j) { q.mu[j] = ly.mu5[j]; q.out[j] = a_x[j].p; }
-                q.lora = a_lora[0].p; q.lora_stride = (int)a_lora[0].halves_per_matrix; q.lora_kq = a_lora[0].kq;
-                q.Dm = info.time_mix_adapter;
-                q.gbar = pre_gbar;
-                launch_cluster = PRE_CLUSTER;
-                const bool tq = q.ln.tp.world > 1;
-                if (split_on) {
-                    if (q.Dm == 32) launch_k(pre6_kernel<2, false, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
-                    else launch_k(pre6_kernel<4, false, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
-                } else if (q.Dm == 32) {
-                    if (tq) launch_k(pre6_kernel<2, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
-                    else launch_k(pre6_kernel<2, false>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
-                } else {
-                    if (tq) launch_k(pre6_kernel<4, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
-                    else launch_k(pre6_kernel<4, false>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
-                }
+            Pre6Params q;
+            memset(&q, 0, sizeof(q));
+            q.ln = ly.ln1;
+            q.ln.trace = tr_next(6);
+            q.W1 = ly.w1_raw; q.W2 = ly.w2_raw;
+            for (int j = 0; j < 5; ++j) { q.mu[j] = ly.mu5[j]; q.out[j] = a_x[j].p; }
+            q.lora = a_lora[0].p; q.lora_stride = (int)a_lora[0].halves_per_matrix; q.lora_kq = a_lora[0].kq;
+            q.Dm = info.time_mix_adapter;
+            q.gbar = pre_gbar;
+            launch_cluster = PRE_CLUSTER;
+            if (split_on) {
+                if (q.Dm == 32) launch_k(pre6_kernel<2, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+                else launch_k(pre6_kernel<4, true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+            } else {
+                if (q.Dm == 32) launch_k(pre6_kernel<2, false>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
+                else launch_k(pre6_kernel<4, false>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, q, KC_LN, s, prof);
             }
         } else {
-            launch_ln(ly.ln1, l > 0 ? 2 * l - 1 : -1);
+            launch_ln(ly.ln1);
         }
-        for (int gi = 0; gi < (int)ly.pre.size(); ++gi) {
-            if (pre_skipped(ly, gi)) continue;
-            if (lora_cc && MT == 1 && l < (int)mega_smallns.size() && gi == 0) {
-                if (!(sk & 2)) launch_k(smalln_kernel, dim3(std::min(num_sms, mega_smallns[l].N)), dim3(CONSUMER_THREADS), 0, mega_smallns[l], KC_OTHER, s, prof);
-                continue;
-            }
-            if (lora_cc && MT == 1 && l < (int)mega_smallks.size() && gi == 1) {
-                if (!(sk & 2)) launch_k(smallk_kernel, dim3(num_sms), dim3(CONSUMER_THREADS), (size_t)16 * 512 * 4, mega_smallks[l], KC_OTHER, s, prof);
-                continue;
-            }
-            gemm(ly.pre[gi]);
-        }
-        if (!(sk & 4)) {
+        for (int gi = 0; gi < (int)ly.pre.size(); ++gi)
+            if (!pre_skipped(ly, gi)) gemm(ly.pre[gi]);
+        {
             // decays / staged rows are sized by the step shape: a slot cannot hold more tokens than the step
-            const size_t wkv_smem = wkv_smem_bytes(info.version, fold_wd2, info.time_decay_adapter, rows);
             WkvParams wp = ly.wkv;
             wp.trace = tr_next(2);
-            const int G = std::max(wkv_stream, cdiv(wkv_slots, 2 * WKV_ST_MAXPOS));
-            if (wkv_stream > 0 && !split_on && MT == 1 && info.version != 7 && G <= wkv_slots) {
-                const size_t sm_b = wkv_stream_smem_bytes(info.version, fold_wd2, info.time_decay_adapter, rows);
-                if (info.version == 6) launch_k(wkv_stream_kernel<6>, dim3(Hl, G), dim3(WKV_ST_THREADS), sm_b, wp, KC_WKV, s, prof, rows);
-                else launch_k(wkv_stream_kernel<5>, dim3(Hl, G), dim3(WKV_ST_THREADS), sm_b, wp, KC_WKV, s, prof, rows);
-            } else if (split_on && MT == 1) {
-                const size_t sm_b = wkv_smem_bytes(info.version, fold_wd2, info.time_decay_adapter, rows, true);
-                switch (info.version) {
-                    case 5: launch_k(wkv_kernel<5, true>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
-                    case 6: launch_k(wkv_kernel<6, true>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
-                    default: launch_k(wkv_kernel<7, true>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
-                }
-            } else
-            switch (info.version) {
-                case 5: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), wkv_smem, wp, KC_WKV, s, prof, rows); break;
-                case 6: launch_k(wkv_kernel<6>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), wkv_smem, wp, KC_WKV, s, prof, rows); break;
-                default: launch_k(wkv_kernel<7>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), wkv_smem, wp, KC_WKV, s, prof, rows); break;
+            const bool sp = split_on && MT == 1;
+            const size_t sm_b = wkv_smem_bytes(info.version, fold_wd2, info.time_decay_adapter, rows, sp);
+            switch (info.version * 2 + (sp ? 1 : 0)) {
+                case 10: launch_k(wkv_kernel<5>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
+                case 11: launch_k(wkv_kernel<5, true>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
+                case 12: launch_k(wkv_kernel<6>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
+                case 13: launch_k(wkv_kernel<6, true>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
+                case 14: launch_k(wkv_kernel<7>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
+                default: launch_k(wkv_kernel<7, true>, dim3(Hl, wkv_slots), dim3(WKV_SA_THREADS), sm_b, wp, KC_WKV, s, prof, rows); break;
             }
         }
         gemm(ly.o);
-        if (world > 1 && !fold) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
-        launch_ln(ly.ln2, 2 * l);
+        if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
+        launch_ln(ly.ln2);
         for (auto& g : ly.ffn) gemm(g);
-        if (world > 1 && !fold) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
+        if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
     }
-    if (!(sk & 1)) {
-        LnOutParams lo = lnout;
-        lo.tp = site(fold ? 2 * L - 1 : -1);
-        if (split_on && MT == 1) launch_k(ln_out_kernel<false, true>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
-        else if (lo.tp.world > 1) launch_k(ln_out_kernel<true>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
-        else launch_k(ln_out_kernel<false>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
+    {
+        if (split_on && MT == 1) launch_k(ln_out_kernel<true>, dim3(rows), dim3(LN_THREADS), 0, lnout, KC_LN, s, prof);
+        else launch_k(ln_out_kernel<false>, dim3(rows), dim3(LN_THREADS), 0, lnout, KC_LN, s, prof);
     }
-    if (MTR > 0 && !(sk & 16)) launch_gemm_chained(head, MTR);
+    if (MTR > 0) launch_gemm_chained(head, MTR);
     if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
 }
 
@@ -1588,22 +1375,19 @@ void b200rwkv_engine::enqueue_keep(cudaStream_t s, int MTR) {
 }
 
 void b200rwkv_engine::run_step(int MT, int MTR) {
-    const bool mega_step = mega_ok && MT == 1 && MTR <= 1;
     if (!use_graph) {
-        if (mega_step) launch_mega(stream);
-        else enqueue_step(stream, MT, MTR, nullptr);
+        enqueue_step(stream, MT, MTR, nullptr);
         enqueue_keep(stream, MTR);
         launch_total += launches_last_step;
         return;
     }
-    const int key = mega_step ? 0 : MT * 8 + MTR;
+    const int key = MT * 8 + MTR;
     auto it = graphs.find(key);
     if (it == graphs.end()) {
         cudaGraph_t g = nullptr;
         CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         try {
-            if (mega_step) launch_mega(stream);
-            else enqueue_step(stream, MT, MTR, nullptr);
+            enqueue_step(stream, MT, MTR, nullptr);
             enqueue_keep(stream, MTR);
         } catch (...) {
             cudaStreamEndCapture(stream, &g);
@@ -1651,27 +1435,6 @@ int b200rwkv_engine::fill_meta(int* m, const std::vector<int>& slots, const std:
     }
     m[0] = T; m[1] = (int)slots.size(); m[2] = R;
     m[4] = (int)++step_seq;   // identical on every rank (SPMD): epoch base of the folded rendezvous
-    // WKV unit shape for the whole-step kernel: slots per (head, group) unit that minimises the
-    // heaviest CTA's stage count under round-robin unit assignment
-    {
-        const int ns = (int)slots.size(), extra = (info.version == 6) ? 1 : 0;
-        int best = 1;
-        long best_cost = -1;
-        for (int gs = 1; gs <= MEGA_MAX_GROUP && ns > 0; ++gs) {
-            const int groups = cdiv(ns, gs), units = Hl * groups;
-            long cost = 0;
-            for (int c = 0; c < std::min(num_sms, units); ++c) {
-                long sum = 0;
-                for (int u = c; u < units; u += num_sms) {
-                    const int grp = u / Hl;
-                    sum += extra + std::min(gs, ns - grp * gs);
-                }
-                cost = std::max(cost, sum);
-            }
-            if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = gs; }
-        }
-        m[3] = best;
-    }
     *R_out = R;
     return T;
 }
@@ -2056,10 +1819,8 @@ static int32_t create_rank(const uint8_t* st, size_t len, int32_t device, int32_
     }
     e->dev = device; e->rank = rank; e->world = world; e->num_sms = prop.multiProcessorCount;
     e->S = max_batch; e->chunk = token_chunk_size; e->precision = precision;
-    if (const char* v = getenv("B200RWKV_GRAPH")) e->use_graph = atoi(v) != 0;
-    if (const char* v = getenv("B200RWKV_PDL")) e->use_pdl = atoi(v) != 0;
-    if (const char* v = getenv("B200RWKV_SKIP")) e->skip_mask = atoi(v);
-    if (const char* v = getenv("B200RWKV_MEGA")) e->use_mega = atoi(v) != 0;
+    if (const char* v = dbg_env("B200RWKV_GRAPH")) e->use_graph = atoi(v) != 0;
+    if (const char* v = dbg_env("B200RWKV_PDL")) e->use_pdl = atoi(v) != 0;
     e->build(f);
     e->loras.clear();            // the LoRA images are only borrowed during the build
     *out = e.release();
@@ -2535,7 +2296,6 @@ static int32_t rank_profile_insitu(b200rwkv_engine* e, int32_t nslot, const int3
     REQUIRE(e && slot && tokens && n_out && types && start_us && end_us && bytes && step_us && reps >= 1 && cap >= 1, B200RWKV_ERR_INVALID,
             "bad argument");
     REQUIRE(nslot >= 1 && nslot <= e->S && nslot <= e->maxT, B200RWKV_ERR_INVALID, "bad argument");
-    REQUIRE(!e->mega_ok, B200RWKV_ERR_UNSUPPORTED, "in-situ profile: per-op chain only");
     std::lock_guard<std::mutex> lk(e->mu);
     CK(cudaSetDevice(e->dev));
     if (!e->d_step_trace) e->d_step_trace = (unsigned long long*)e->dalloc((size_t)b200rwkv_engine::STEP_TRACE_MAX * b200rwkv_engine::STEP_TRACE_ROW * 8, true);
@@ -2771,31 +2531,23 @@ int32_t b200rwkv_debug_read(b200rwkv_engine* e, const char* name, float* out, si
     }
 }
 
-// Test/profiling aid: per-phase globaltimer stamps of the last whole-step kernel (needs
-// B200RWKV_TRACE=1 at creation).  out: [4][nphase][2] u64; types: [nphase] phase types.
+// Profiling aid: the raw stamp rows of the most recent traced replay (b200rwkv_profile_insitu): one row of 512 uint64 per
+// launch -- [0..7] globaltimer stamps of CTA 0 (entry, past griddepcontrol.wait, phase marks, exit), then {SM id, last MMA
+// issued, exit} of every projection CTA (or {entry, released, phase 1 done} of every CTA of the RWKV-6 front-half kernel).
 int32_t b200rwkv_debug_trace(b200rwkv_engine* e, uint64_t* out, size_t cap, int32_t* types, int32_t* nphase) {
-    if (!e || !out || !types || !nphase) return B200RWKV_ERR_INVALID;
-    if (e->d_step_trace && !(e->mega_ok && e->mega.trace)) {
-        // per-op chain: one row of 8 stamps per launch of the last captured step shape
-        const size_t nl = e->step_trace_types.size();
-        const size_t row = b200rwkv_engine::STEP_TRACE_ROW;
-        if (cap < nl * row) return B200RWKV_ERR_INVALID;
-        cudaSetDevice(e->dev);
-        cudaStreamSynchronize(e->stream);
-        if (cudaMemcpy(out, e->d_step_trace, nl * row * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return B200RWKV_ERR_CUDA;
-        for (size_t i = 0; i < nl; ++i) types[i] = e->step_trace_types[i];
-        *nphase = (int32_t)nl;
-        return B200RWKV_OK;
-    }
-    if (!e->mega_ok || !e->mega.trace) { g_err = "no trace (set B200RWKV_TRACE=1)"; return B200RWKV_ERR_INVALID; }
-    const size_t n = (size_t)4 * e->mega.nphase * 12;
-    if (cap < n) return B200RWKV_ERR_INVALID;
-    cudaSetDevice(e->dev);
-    cudaStreamSynchronize(e->stream);
-    if (cudaMemcpy(out, e->mega.trace, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return B200RWKV_ERR_CUDA;
-    for (int i = 0; i < e->mega.nphase; ++i) types[i] = e->mega_phase_types[i];
-    *nphase = e->mega.nphase;
-    return B200RWKV_OK;
+    API_BEGIN(e)
+    REQUIRE(e && out && types && nphase, B200RWKV_ERR_INVALID, "null argument");
+    REQUIRE(e->d_step_trace && !e->step_trace_types.empty(), B200RWKV_ERR_INVALID, "no trace: call b200rwkv_profile_insitu first");
+    std::lock_guard<std::mutex> lk(e->mu);
+    const size_t nl = e->step_trace_types.size();
+    const size_t row = b200rwkv_engine::STEP_TRACE_ROW;
+    REQUIRE(cap >= nl * row, B200RWKV_ERR_INVALID, "trace buffer too small");
+    CK(cudaSetDevice(e->dev));
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, e->d_step_trace, nl * row * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nl; ++i) types[i] = e->step_trace_types[i];
+    *nphase = (int32_t)nl;
+    API_END
 }
 
 // Profiling aid: time one projection launch class in isolation, round-robin over the layers so
@@ -2842,6 +2594,7 @@ int32_t b200rwkv_debug_gemm_time(b200rwkv_engine* e, int32_t which, int32_t reps
     API_END
 }
 
+#ifdef B200RWKV_DEBUG
 // Streaming micro-benchmark (see streamtest.cuh).  kind 0: vector loads; kind 1: bulk-TMA ring.
 int32_t b200rwkv_debug_stream(int32_t device, int32_t kind, double gbytes, int32_t stage_bytes, int32_t nstage, int32_t use_hint,
                               int32_t consumer, int32_t split, int32_t producers, int32_t reps, float* ms_out) {
@@ -2931,6 +2684,8 @@ int32_t b200rwkv_debug_prefetch(int32_t device, double mbytes, int32_t consumers
     cudaEventDestroy(a); cudaEventDestroy(b); cudaEventDestroy(c);
     API_END
 }
+
+#endif   // B200RWKV_DEBUG
 
 // ---- exported SPMD entries: one rank, or all ranks of an in-process tensor-parallel engine at once ----
 #define RANKS(e, call_r) ((e) && (e)->group ? (e)->group->spmd([&](int r_) -> int32_t { b200rwkv_engine* er = (e)->group->ranks[r_]; (void)er; return call_r; }) : [&]() -> int32_t { b200rwkv_engine* er = (e); const int r_ = 0; (void)r_; return call_r; }())

@@ -197,16 +197,9 @@ __device__ __forceinline__ void gemm_mma_role(const GemmParams& p, const int b0,
 // Epilogue role (4 warps = 128 threads, thread t owns output row t of the tile): drain TMEM,
 // deterministic cross-CTA reduction of split tiles, fused epilogue.
 // ---------------------------------------------------------------------------------------
-// FIN (opt-in, B200RWKV_FINISHER=1; written at the end of round 1, NOT yet run on hardware): "designated finisher" instead
-// of "last arriver".  A tile shared by several CTAs is met by the CTA holding its first k blocks at the END of that CTA's
-// range and by every other contributor at the START of theirs, so the finisher is known statically: the others write
-// their partials and signal with a one-way `red.release`; the finisher polls and pulls the first partner partial into
-// registers while its own MMAs still run, then adds in the same fixed slot order as the default path (bit-identical
-// results).  This takes the atomic round trip and the dependent partial loads off the tail of stream-K launches
-// (profiles/r01_findings.md §7: +5..9 us on 148-CTA launches), which is what tensor-parallel shapes need.
-// SPLIT (opt-in B200RWKV_SPLIT_ACT=1, MT = 2): the two token tiles are the hi and lo halves of the SAME 16 tokens
+// SPLIT (precision 1, MT = 2): the two token tiles are the hi and lo halves of the SAME 16 tokens
 // (common.cuh split_h): the accumulator tiles are added before the epilogue and A16 outputs are written as hi / lo again.
-template <int MT, bool FIN = false, bool SPLIT = false>
+template <int MT, bool SPLIT = false>
 __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const int cta, const int G, const int b0, const int b1,
                                                    const uint32_t tfull_bar, const uint32_t tempty_bar, const uint32_t tmem_base,
                                                    unsigned& segcount, const int nrows, volatile int* s_last_p,
@@ -226,27 +219,6 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
         const GemmSeg& sg = p.seg[w.seg];
         const unsigned acc = segcount & 1u, use = segcount >> 1;
         constexpr int ROWF = 16 * MT;
-        float4 pf[MT][4];
-        if (FIN) {
-            const unsigned tb0f = (unsigned)(sg.blk_begin + w.tile_local * sg.KB);
-            const int cf = (int)(((unsigned long long)(tb0f + 1) * (unsigned)G - 1) / TB);
-            const int cl = (int)(((unsigned long long)(tb0f + sg.KB) * (unsigned)G - 1) / TB);
-            if (cl > cf && cta == cf) {
-                // finisher: the partner partials were published long ago; fetch slot 1 while our own MMAs still run
-                const int gt = sg.tile_begin + w.tile_local;
-                if (tid == 0) {
-                    SpinGuard sg_;
-                    unsigned seen;
-                    while ((seen = ld_acquire_gpu(p.counters + gt)) < (unsigned)(cl - cf)) sg_.poll(8u, (unsigned)gt, (unsigned)(cl - cf), seen);
-                }
-                named_bar_sync(3, GEMM_EPI_THREADS);
-                const float* w1 = p.ws + ((size_t)gt * p.max_contrib + 1) * (GEMM_BN * ROWF) + (size_t)tid * ROWF;
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) pf[mt][j] = __ldcg(reinterpret_cast<const float4*>(w1 + mt * 16 + 4 * j));
-            }
-        }
         mbar_wait(tfull_bar + acc * 8, use & 1u, 13);
         stamp(8);
         tc_fence_after();
@@ -265,44 +237,7 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
         const int ncontrib = c_last - c_first + 1;
         const int gtile = sg.tile_begin + w.tile_local;
         bool do_epilogue = true;
-        if (FIN && ncontrib > 1) {
-            if (cta != c_first) {
-                float* wsl = p.ws + ((size_t)gtile * p.max_contrib + (cta - c_first)) * (GEMM_BN * ROWF) + (size_t)tid * ROWF;
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(wsl + mt * 16 + j) = make_float4(v[mt][j], v[mt][j + 1], v[mt][j + 2], v[mt][j + 3]);
-                named_bar_sync(3, GEMM_EPI_THREADS);       // every thread's partial stores happen-before thread 0's release
-                if (tid == 0) red_add_release_gpu(p.counters + gtile, 1u);
-                do_epilogue = false;
-            } else {
-                // own accumulator (slot 0) + slot 1 (prefetched) + slots 2.. in order: same sum order as the default path
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        v[mt][4 * j] += pf[mt][j].x; v[mt][4 * j + 1] += pf[mt][j].y;
-                        v[mt][4 * j + 2] += pf[mt][j].z; v[mt][4 * j + 3] += pf[mt][j].w;
-                    }
-                for (int s = 2; s < ncontrib; ++s) {
-                    const float* w_ = p.ws + ((size_t)gtile * p.max_contrib + s) * (GEMM_BN * ROWF) + (size_t)tid * ROWF;
-                    float4 q[MT][4];
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) q[mt][j] = __ldcg(reinterpret_cast<const float4*>(w_ + mt * 16 + 4 * j));
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            v[mt][4 * j] += q[mt][j].x; v[mt][4 * j + 1] += q[mt][j].y;
-                            v[mt][4 * j + 2] += q[mt][j].z; v[mt][4 * j + 3] += q[mt][j].w;
-                        }
-                }
-                if (tid == 0) p.counters[gtile] = 0;     // ready for the next launch (its arrivals are a kernel boundary away)
-            }
-        } else if (ncontrib > 1) {
+        if (ncontrib > 1) {
             float* wsl = p.ws + ((size_t)gtile * p.max_contrib + (cta - c_first)) * (GEMM_BN * ROWF) + (size_t)tid * ROWF;
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
@@ -433,7 +368,7 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
 // ---------------------------------------------------------------------------------------
 // stand-alone kernel: warps 0-3 epilogue, warp 4 MMA issuer (+ TMEM allocation), warp 5 TMA producer
 // ---------------------------------------------------------------------------------------
-template <int MT, int RING = 0, bool FIN = false, bool SPLIT = false>
+template <int MT, int RING = 0, bool SPLIT = false>
 __global__ void __launch_bounds__(GEMM_THREADS, RING == 1 ? 2 : 1) gemm_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<MT, RING>;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -550,7 +485,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, RING == 1 ? 2 : 1) gemm_kernel(c
         pdl_wait();
         if (tid == 0) stamp(5);
         unsigned segcount = 0;
-        gemm_epilogue_role<MT, FIN, SPLIT>(p, cta, G, b0, b1, tfull_bar, tempty_bar, tmem_base, segcount, *p.nrows, &s_last, tr);
+        gemm_epilogue_role<MT, SPLIT>(p, cta, G, b0, b1, tfull_bar, tempty_bar, tmem_base, segcount, *p.nrows, &s_last, tr);
         if (tid == 0) stamp(6);
     }
     tc_fence_before();

@@ -46,7 +46,6 @@ struct LnMixParams {
     float* commit_dst;      // [S, C] or null
     const float* commit_src;    // [T, C]
     unsigned long long* trace;  // profiling aid (null in production)
-    TpFold tp;                  // folded tensor-parallel rendezvous (world <= 1: none)
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -112,12 +111,12 @@ __device__ __forceinline__ void residual_row(const ResidualSrc& r, const int t, 
 }
 
 // two-pass mean / rstd of a row held in registers
-template <int NV, bool MEGA>
+template <int NV>
 __device__ __forceinline__ void row_stats(const int C, const float4 (&a)[NV], float* red, float& mean, float& rstd) {
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) s += (a[j].x + a[j].y) + (a[j].z + a[j].w);
-    mean = block_sum<MEGA>(s, red) / (float)C;
+    mean = block_sum(s, red) / (float)C;
     float s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -127,7 +126,7 @@ __device__ __forceinline__ void row_stats(const int C, const float4 (&a)[NV], fl
             s2 += (dx * dx + dy * dy) + (dz * dz + dw * dw);
         }
     }
-    const float var = block_sum<MEGA>(s2, red) / (float)C;
+    const float var = block_sum(s2, red) / (float)C;
     rstd = 1.0f / sqrtf(var + LN_EPS);
 }
 
@@ -140,7 +139,7 @@ __device__ __forceinline__ float4 ln_apply(const float4 a, const float mean, con
     return o;
 }
 
-template <int NV, bool MEGA>
+template <int NV>
 __device__ __forceinline__ void ln_mix_row_nv(const LnMixParams& p, const int t, float* red, unsigned long long* stamps = nullptr) {
     auto stamp = [&](int i) { if (stamps && threadIdx.x == 0) stamps[i] = globaltimer_ns(); };
     stamp(0);
@@ -172,12 +171,12 @@ __device__ __forceinline__ void ln_mix_row_nv(const LnMixParams& p, const int t,
     }
     float mean, rstd;
     stamp(3);
-    row_stats<NV, MEGA>(C, a, red, mean, rstd);
+    row_stats<NV>(C, a, red, mean, rstd);
     stamp(4);
     if (prev_t >= 0) {          // multi-token slot (prefill): previous token's LN output, recomputed
         float pmean, prstd;
         residual_row<NV>(r, prev_t, pv);
-        row_stats<NV, MEGA>(C, pv, red, pmean, prstd);
+        row_stats<NV>(C, pv, red, pmean, prstd);
 #pragma unroll
         for (int j = 0; j < NV; ++j) pv[j] = ln_apply(pv[j], pmean, prstd, w[j], b[j]);
     }
@@ -218,27 +217,24 @@ __device__ __forceinline__ void ln_mix_row_nv(const LnMixParams& p, const int t,
     }
 }
 
-template <bool MEGA>
 __device__ __forceinline__ void ln_mix_row(const LnMixParams& p, const int t, float* red, unsigned long long* stamps = nullptr) {
     const int nv = (p.C + 4 * LN_THREADS - 1) / (4 * LN_THREADS);
-    if (nv <= 1) ln_mix_row_nv<1, MEGA>(p, t, red);
-    else if (nv == 2) ln_mix_row_nv<2, MEGA>(p, t, red);
-    else if (nv <= 4 || MEGA) ln_mix_row_nv<4, MEGA>(p, t, red, stamps);      // the whole-step kernel caps C at 4096
-    else ln_mix_row_nv<8, MEGA>(p, t, red);
+    if (nv <= 1) ln_mix_row_nv<1>(p, t, red);
+    else if (nv == 2) ln_mix_row_nv<2>(p, t, red);
+    else if (nv <= 4) ln_mix_row_nv<4>(p, t, red, stamps);
+    else ln_mix_row_nv<8>(p, t, red);
     if (stamps && threadIdx.x == 0) stamps[6] = globaltimer_ns();
 }
 
-template <bool TPF = false>
 __global__ void __launch_bounds__(LN_THREADS) ln_mix_kernel(const __grid_constant__ LnMixParams p) {
     __shared__ float red[32];
     trace_stamp(p.trace, 0);
     pdl_launch_dependents();
     pdl_wait();
-    if (TPF) tp_rendezvous(p.tp);
     trace_stamp(p.trace, 1);
     const int t = blockIdx.x;
     if (t >= p.meta.T()) return;
-    ln_mix_row<false>(p, t, red);
+    ln_mix_row(p, t, red);
     trace_stamp(p.trace, 7);
 }
 
@@ -255,7 +251,7 @@ struct EmbedParams {
     float* x_out;          // [T, C]
 };
 
-template <int NV, bool MEGA>
+template <int NV>
 __device__ __forceinline__ void embed_row_nv(const EmbedParams& p, const int t, float* red) {
     const int C = p.C;
     int tok = p.meta.tok()[t];
@@ -276,7 +272,7 @@ __device__ __forceinline__ void embed_row_nv(const EmbedParams& p, const int t, 
         }
     }
     float mean, rstd;
-    row_stats<NV, MEGA>(C, a, red, mean, rstd);
+    row_stats<NV>(C, a, red, mean, rstd);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int c = 4 * (threadIdx.x + LN_THREADS * j);
@@ -284,13 +280,12 @@ __device__ __forceinline__ void embed_row_nv(const EmbedParams& p, const int t, 
     }
 }
 
-template <bool MEGA>
 __device__ __forceinline__ void embed_row(const EmbedParams& p, const int t, float* red) {
     const int nv = (p.C + 4 * LN_THREADS - 1) / (4 * LN_THREADS);
-    if (nv <= 1) embed_row_nv<1, MEGA>(p, t, red);
-    else if (nv == 2) embed_row_nv<2, MEGA>(p, t, red);
-    else if (nv <= 4 || MEGA) embed_row_nv<4, MEGA>(p, t, red);      // the whole-step kernel caps C at 4096
-    else embed_row_nv<8, MEGA>(p, t, red);
+    if (nv <= 1) embed_row_nv<1>(p, t, red);
+    else if (nv == 2) embed_row_nv<2>(p, t, red);
+    else if (nv <= 4) embed_row_nv<4>(p, t, red);
+    else embed_row_nv<8>(p, t, red);
 }
 
 __global__ void __launch_bounds__(LN_THREADS) embed_ln0_kernel(const __grid_constant__ EmbedParams p) {
@@ -299,7 +294,7 @@ __global__ void __launch_bounds__(LN_THREADS) embed_ln0_kernel(const __grid_cons
     pdl_wait();
     const int t = blockIdx.x;
     if (t >= p.meta.T()) return;
-    embed_row<false>(p, t, red);
+    embed_row(p, t, red);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -322,11 +317,10 @@ struct LnOutParams {
     int kq_tile;
     float* commit_dst;
     const float* commit_src;
-    float* hidden_out;      // optional [T, C]: updated residual (debug / states endpoint)
-    TpFold tp;              // folded tensor-parallel rendezvous (world <= 1: none)
+    float* hidden_out;      // optional [T, C]: updated residual (hidden states of the embeddings route)
 };
 
-template <int NV, bool MEGA, bool SPLIT = false>
+template <int NV, bool SPLIT = false>
 __device__ __forceinline__ void ln_out_row_nv(const LnOutParams& p, const int t, float* red) {
     const int C = p.C;
     const int slot = p.meta.tok_slot()[t];
@@ -353,7 +347,7 @@ __device__ __forceinline__ void ln_out_row_nv(const LnOutParams& p, const int t,
     }
     if (row < 0) return;
     float mean, rstd;
-    row_stats<NV, MEGA>(C, a, red, mean, rstd);
+    row_stats<NV>(C, a, red, mean, rstd);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int c = 4 * (threadIdx.x + LN_THREADS * j);
@@ -375,24 +369,23 @@ __device__ __forceinline__ void ln_out_row_nv(const LnOutParams& p, const int t,
     }
 }
 
-template <bool MEGA, bool SPLIT = false>
+template <bool SPLIT = false>
 __device__ __forceinline__ void ln_out_row(const LnOutParams& p, const int t, float* red) {
     const int nv = (p.C + 4 * LN_THREADS - 1) / (4 * LN_THREADS);
-    if (nv <= 1) ln_out_row_nv<1, MEGA, SPLIT>(p, t, red);
-    else if (nv == 2) ln_out_row_nv<2, MEGA, SPLIT>(p, t, red);
-    else if (nv <= 4 || MEGA) ln_out_row_nv<4, MEGA, SPLIT>(p, t, red);      // the whole-step kernel caps C at 4096
-    else ln_out_row_nv<8, MEGA, SPLIT>(p, t, red);
+    if (nv <= 1) ln_out_row_nv<1, SPLIT>(p, t, red);
+    else if (nv == 2) ln_out_row_nv<2, SPLIT>(p, t, red);
+    else if (nv <= 4) ln_out_row_nv<4, SPLIT>(p, t, red);
+    else ln_out_row_nv<8, SPLIT>(p, t, red);
 }
 
-template <bool TPF = false, bool SPLIT = false>
+template <bool SPLIT = false>
 __global__ void __launch_bounds__(LN_THREADS) ln_out_kernel(const __grid_constant__ LnOutParams p) {
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
-    if (TPF) tp_rendezvous(p.tp);
     const int t = blockIdx.x;
     if (t >= p.meta.T()) return;
-    ln_out_row<false, SPLIT>(p, t, red);
+    ln_out_row<SPLIT>(p, t, red);
 }
 
 }  // namespace b200

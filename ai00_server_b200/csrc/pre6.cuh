@@ -122,13 +122,13 @@ __device__ __forceinline__ void slice_stats(cg::cluster_group& cl, const unsigne
                                             float* red, float* xch, float& mean, float& rstd) {
     const int Cs = C / PRE_CLUSTER;
     const float s = act ? (a.x + a.y) + (a.z + a.w) : 0.f;
-    const float mi = block_sum<false>(s, red) / (float)Cs;
+    const float mi = block_sum(s, red) / (float)Cs;
     float s2 = 0.f;
     if (act) {
         const float dx = a.x - mi, dy = a.y - mi, dz = a.z - mi, dw = a.w - mi;
         s2 = (dx * dx + dy * dy) + (dz * dz + dw * dw);
     }
-    const float m2i = block_sum<false>(s2, red);
+    const float m2i = block_sum(s2, red);
     if (threadIdx.x < PRE_CLUSTER) {
         float* dst = cl.map_shared_rank(xch, threadIdx.x);
         dst[rank] = mi;
@@ -227,7 +227,7 @@ __device__ __forceinline__ void pre_ln_slice(const LnMixParams& p, const int t, 
 }
 
 // LN stage alone (channel mix of every version, time mix of RWKV-5/7): 16 clusters x 8, no grid barrier
-template <bool TPF = false, bool SPLIT = false>
+template <bool SPLIT = false>
 __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __grid_constant__ LnMixParams p) {
     __shared__ float red[32];
     __shared__ float xch[2][2 * PRE_CLUSTER];
@@ -238,7 +238,6 @@ __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __gri
     pdl_launch_dependents();
     const PreLnStatic<6> st = pre_ln_static<6>(p, t, rank);
     pdl_wait();
-    if (TPF) tp_rendezvous(p.tp);
     trace_stamp(p.trace, 1);
     if (t >= st.T) return;                // uniform over the cluster
     pre_ln_slice<6, SPLIT>(p, t, cl, rank, st, red, xch);
@@ -247,7 +246,7 @@ __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __gri
 }
 
 // KD = Dm / 16
-template <int KD, bool TPF = false, bool SPLIT = false>
+template <int KD, bool SPLIT = false>
 __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_constant__ Pre6Params p) {
     __shared__ float red[32];
     __shared__ float xch[2][2 * PRE_CLUSTER];
@@ -312,7 +311,6 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
         mu3[i] = ok ? *reinterpret_cast<const float2*>(p.mu[j] + tc0[i] + tig * 2) : make_float2(0.f, 0.f);
     }
     pdl_wait();
-    if (TPF) tp_rendezvous(p.ln.tp);
     trace_stamp(tr, 1);
     cta_stamp(1);
     const int T = min(st.T, 16);

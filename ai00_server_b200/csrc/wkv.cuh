@@ -77,22 +77,14 @@ struct WkvShared {
 // `pre`: optional shared-memory copy of the head's per-token vectors, [array][token][64] with arrays
 // r, k, v, g (, w, a, nu for v7) and `pre_stride` floats between arrays (whole-step kernel: gathered
 // once per WKV unit so the per-token loop never waits on L2).
-// KC: key columns per thread (4: 256 threads per head, 8: 128 threads per head); the thread's patch is m[e][f] =
-// M[4*ig + e][KC*j4 + f].
-// SUB = 1: the caller is one of two independent 128-thread halves of a 256-thread CTA (wkv_stream_kernel): thread index
-// and barriers are local to the half (named barrier 1 + half).  Not available for VER 7 (its two-warp norm barrier).
-template <bool MEGA, int SUB>
-__device__ __forceinline__ void wkv_sync() {
-    if (SUB) asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory");
-    else cta_sync<MEGA>();
-}
-template <int VER, bool MEGA, int KC = 4, int SUB = 0, bool SPLIT = false>
+// KC: key columns per thread (8: 128 threads per head); the thread's patch is m[e][f] = M[4*ig + e][KC*j4 + f].
+template <int VER, int KC = 8, bool SPLIT = false>
 __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const int t0, const int nt, float (&m)[4][KC],
                                          WkvShared& sm, const float* w_local, const int lt0, const float* pre = nullptr,
                                          const int pre_stride = 0, const float* statics = nullptr) {
     // `statics`: optional shared-memory copy of this head's [ln_x weight 64][ln_x bias 64][time_first 64], staged by the
     // caller before it waited on the producer kernel (keeps three L2 round trips off the per-step chain)
-    const int tid = SUB ? (int)(threadIdx.x & 127) : (int)threadIdx.x;
+    const int tid = (int)threadIdx.x;
     constexpr int LANES = WKV_N / KC;  // threads that share a value row (reduction width)
     const int ig = tid / LANES;        // value rows 4*ig .. 4*ig+3
     const int j4 = tid % LANES;        // key cols  KC*j4 .. KC*j4+KC-1
@@ -137,7 +129,7 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
             }
             sm.r[c] = r; sm.k[c] = k; sm.v[c] = v; sm.w[c] = w;
         }
-        wkv_sync<MEGA, SUB>();
+        __syncthreads();
 
         float rr[KC], kk_[KC], ww[KC];
 #pragma unroll
@@ -191,12 +183,12 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
         for (int off = LANES / 2; off > 0; off >>= 1)
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] += __shfl_xor_sync(0xffffffffu, o[e], off);
-        wkv_sync<MEGA, SUB>();              // all reads of sm.o (-kk) done before it is overwritten
+        __syncthreads();              // all reads of sm.o (-kk) done before it is overwritten
         if (j4 == 0) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) sm.o[ig * 4 + e] = o[e];
         }
-        wkv_sync<MEGA, SUB>();
+        __syncthreads();
 
         // ---- GroupNorm over the head + gate, warp 0: 2 channels per lane ----
         if (tid < 32) {
@@ -231,7 +223,7 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
                 p.out[a16_index(t, ch + tid + 32, p.kq_tile)] = f2h_sat(y1);
             }
         }
-        wkv_sync<MEGA, SUB>();              // shared vectors are rewritten by the next token
+        __syncthreads();              // shared vectors are rewritten by the next token
     }
 }
 
@@ -395,7 +387,7 @@ __global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_con
         w_local = wl;
     }
     __syncthreads();
-    wkv_slot<VER, false, KC, 0, SPLIT>(p, h, t0, nt, m, sm, w_local, 0, staged ? pre_s : nullptr, WKV_STAGE_TOK * WKV_N, statics);
+    wkv_slot<VER, KC, SPLIT>(p, h, t0, nt, m, sm, w_local, 0, staged ? pre_s : nullptr, WKV_STAGE_TOK * WKV_N, statics);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
 #pragma unroll
@@ -403,164 +395,6 @@ __global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_con
             __stcs(reinterpret_cast<float4*>(M + (ig * 4 + e) * WKV_N + j4 * KC + q * 4),
                    make_float4(m[e][q * 4], m[e][q * 4 + 1], m[e][q * 4 + 2], m[e][q * 4 + 3]));
     trace_stamp(p.trace, 7);
-}
-
-// ---------------------------------------------------------------------------------------
-// Streaming variant (opt-in, B200RWKV_WKV_STREAM=G; written at the end of round 1, NOT yet run on hardware).
-// Measured problem of the kernel above (profiles/r01_findings.md §9): with one (head, slot) per CTA all 1024 CTAs read
-// their 16 KB of state, compute and write in lockstep -- a 16 MB read burst, an idle gap, a 16 MB write burst, 12.4 us
-// for 33.6 MB -- and every CTA pulls its own copy of the head's 16 KB decay-LoRA slice through L2 (16 MB per layer).
-// Here a CTA owns a head and every G-th slot; its two 128-thread halves walk alternate slots of that list independently
-// (own named barrier, own staging buffers), so loads of one slot overlap the arithmetic and stores of another on the
-// same SM, and the decay-LoRA slice, ln_x and time_first are staged once per CTA.  RWKV-5/6 only.
-// ---------------------------------------------------------------------------------------
-constexpr int WKV_ST_THREADS = 256;
-constexpr int WKV_ST_MAXPOS = 4;        // slots per half (=> G >= nslots / 8)
-
-__host__ __device__ inline size_t wkv_stream_sub_bytes(int ver, bool fold, int Dd, int max_tokens) {
-    size_t b = 0;
-    if (fold) b += (size_t)max_tokens * WKV_N * 4 + ((((size_t)WKV_STAGE_TOK * Dd * 2) + 15) & ~(size_t)15) + 2 * WKV_N * 4;
-    b += (size_t)wkv_stage_arrays(ver, fold) * WKV_STAGE_TOK * WKV_N * 4;
-    return (b + 15) & ~(size_t)15;
-}
-__host__ __device__ inline size_t wkv_stream_smem_bytes(int ver, bool fold, int Dd, int max_tokens) {
-    return (fold ? (size_t)WKV_N * Dd * 2 : 0) + 3 * WKV_N * 4 + 2 * wkv_stream_sub_bytes(ver, fold, Dd, max_tokens) + 64;
-}
-
-template <int VER>
-__global__ void __launch_bounds__(WKV_ST_THREADS, 3) wkv_stream_kernel(const __grid_constant__ WkvParams p, const int max_tokens) {
-    static_assert(VER == 5 || VER == 6, "streaming WKV: RWKV-5/6");
-    constexpr int KC = WKV_SA_KC, LANES = WKV_N / KC, NT = 128;
-    __shared__ WkvShared smv[2];
-    extern __shared__ __align__(16) uint8_t wkv_dyn[];
-    pdl_launch_dependents();
-    const int h = blockIdx.x, G = gridDim.y;
-    const int tid = threadIdx.x, half = tid >> 7, lt = tid & 127;
-    const int ig = lt / LANES, j4 = lt % LANES;
-    const int ch = h * WKV_N;
-    const bool fold = (VER == 6) && p.wd2t != nullptr;
-    const int Dd = fold ? p.Dd : 0;
-    const int na = wkv_stage_arrays(VER, fold);
-    // shared by both halves: decay-LoRA slice, statics
-    __half* wt = reinterpret_cast<__half*>(wkv_dyn);
-    float* statics = reinterpret_cast<float*>(wkv_dyn + (fold ? (size_t)WKV_N * Dd * 2 : 0));
-    // per half
-    uint8_t* sub = reinterpret_cast<uint8_t*>(statics + 3 * WKV_N) + (size_t)half * wkv_stream_sub_bytes(VER, fold, Dd, max_tokens);
-    float* wl = nullptr;
-    __half* ds = nullptr;
-    float* part = nullptr;
-    if (fold) {
-        wl = reinterpret_cast<float*>(sub);
-        ds = reinterpret_cast<__half*>(wl + (size_t)max_tokens * WKV_N);
-        part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ds) + ((((size_t)WKV_STAGE_TOK * Dd * 2) + 15) & ~(size_t)15));
-        sub = reinterpret_cast<uint8_t*>(part + 2 * WKV_N);
-    }
-    float* pre_s = reinterpret_cast<float*>(sub);
-    auto sub_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); };
-
-    // ---- before the wait: weights, statics, this half's slot list ----
-    if (fold) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.wd2t + (size_t)h * WKV_N * Dd);
-        uint4* dst = reinterpret_cast<uint4*>(wt);
-        for (int i = tid; i < WKV_N * Dd / 8; i += WKV_ST_THREADS) dst[i] = src[i];
-    }
-    if (tid < 3 * WKV_N) {
-        const int a = tid >> 6, c = tid & (WKV_N - 1);
-        statics[tid] = a == 0 ? p.lnx_w[ch + c] : (a == 1 ? p.lnx_b[ch + c] : p.u[ch + c]);
-    }
-    const float bias = fold ? p.decay_bias[ch + (lt & (WKV_N - 1))] : 0.f;
-    const int nslots = p.meta.nslots();
-    int sl_slot[WKV_ST_MAXPOS], sl_t0[WKV_ST_MAXPOS], sl_nt[WKV_ST_MAXPOS];
-#pragma unroll
-    for (int q = 0; q < WKV_ST_MAXPOS; ++q) {
-        const int si = (int)blockIdx.y + (half + 2 * q) * G;
-        const bool live = si < nslots;
-        sl_slot[q] = live ? p.meta.slot_id()[si] : -1;
-        sl_t0[q] = live ? p.meta.slot_start()[si] : 0;
-        sl_nt[q] = live ? p.meta.slot_count()[si] : 0;
-    }
-    pdl_wait();
-    __syncthreads();          // decay-LoRA slice and statics visible to both halves; the halves run independently from here
-
-#pragma unroll
-    for (int q = 0; q < WKV_ST_MAXPOS; ++q) {
-        const int slot = sl_slot[q], t0 = sl_t0[q], nt = sl_nt[q];
-        if (slot >= 0) {          // uniform over the half (slot lists are in increasing order: a dead entry ends the list)
-            float* M = p.state + ((size_t)slot * p.H + h) * (WKV_N * WKV_N);
-            float m[4][KC];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-#pragma unroll
-                for (int qq = 0; qq < KC / 4; ++qq) {
-                    const float4 v4 = __ldcs(reinterpret_cast<const float4*>(M + (ig * 4 + e) * WKV_N + j4 * KC + qq * 4));
-                    m[e][qq * 4] = v4.x; m[e][qq * 4 + 1] = v4.y; m[e][qq * 4 + 2] = v4.z; m[e][qq * 4 + 3] = v4.w;
-                }
-            const bool staged = nt <= WKV_STAGE_TOK;
-            if (staged) {
-                constexpr int UMAX = WKV_STAGE_ARRAYS * WKV_STAGE_TOK * WKV_N / NT;      // 14
-                const int per = nt * WKV_N, total = na * per;
-                const int ndd = fold ? nt * Dd : 0;
-#pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
-                    float val[UMAX / 2];
-#pragma unroll
-                    for (int u = 0; u < UMAX / 2; ++u) {
-                        const int i = lt + (hb * (UMAX / 2) + u) * NT;
-                        val[u] = 0.f;
-                        if (i < total) {
-                            const int a = i / per, rem = i - a * per;
-                            const size_t at = (size_t)(t0 + (rem >> 6)) * p.ld + ch + (rem & (WKV_N - 1));
-                            const float* src = a == 0 ? p.r : a == 1 ? p.k : a == 2 ? p.v : a == 3 ? p.g : p.w;
-                            if (src) val[u] = src[at];
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < UMAX / 2; ++u) {
-                        const int i = lt + (hb * (UMAX / 2) + u) * NT;
-                        if (i < total) {
-                            const int a = i / per, rem = i - a * per;
-                            pre_s[a * (WKV_STAGE_TOK * WKV_N) + rem] = val[u];
-                        }
-                    }
-                }
-                for (int i = lt; i < ndd; i += NT) {
-                    const int tt = i / Dd;
-                    ds[i] = p.d1[a16_index(t0 + tt, i - tt * Dd, p.d1_kq)];
-                }
-            }
-            const float* w_local = nullptr;
-            if (fold) {
-                const int c = lt & (WKV_N - 1), qk = lt >> 6;
-                const int kq0 = qk * (Dd >> 1), kq1 = kq0 + (Dd >> 1);
-                for (int tt = 0; tt < nt; ++tt) {
-                    sub_sync();
-                    const __half* dt = staged ? ds + tt * Dd : ds;
-                    if (!staged) {
-                        for (int k = lt; k < Dd; k += NT) ds[k] = p.d1[a16_index(t0 + tt, k, p.d1_kq)];
-                        sub_sync();
-                    }
-                    float acc0 = 0.f, acc1 = 0.f;
-                    for (int k = kq0; k < kq1; k += 2) {
-                        acc0 = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(dt[k]), acc0);
-                        acc1 = fmaf(__half2float(wt[(k + 1) * WKV_N + c]), __half2float(dt[k + 1]), acc1);
-                    }
-                    part[qk * WKV_N + c] = acc0 + acc1;
-                    sub_sync();
-                    if (lt < WKV_N) wl[tt * WKV_N + c] = expf(-expf(bias + (part[c] + part[WKV_N + c])));
-                }
-                w_local = wl;
-            }
-            sub_sync();
-            wkv_slot<VER, false, KC, 1>(p, h, t0, nt, m, smv[half], w_local, 0, staged ? pre_s : nullptr, WKV_STAGE_TOK * WKV_N, statics);
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-#pragma unroll
-                for (int qq = 0; qq < KC / 4; ++qq)
-                    __stcs(reinterpret_cast<float4*>(M + (ig * 4 + e) * WKV_N + j4 * KC + qq * 4),
-                           make_float4(m[e][qq * 4], m[e][qq * 4 + 1], m[e][qq * 4 + 2], m[e][qq * 4 + 3]));
-            sub_sync();           // staging buffers are rewritten by this half's next slot
-        }
-    }
 }
 
 }  // namespace b200

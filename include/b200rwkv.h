@@ -100,6 +100,7 @@ typedef struct {
 int32_t b200rwkv_create_ex(const uint8_t* st, size_t len, const b200rwkv_options* opt, b200rwkv_engine** out);
 
 /* Tensor-parallel construction, one process per GPU (head / column parallel).
+ * (The in-process alternative -- one handle, all ranks inside -- is b200rwkv_create_ex above.)
  * Every rank calls create_tp with the same model, then exchanges the opaque handle blobs
  * (b200rwkv_tp_export on each rank, all-gathered by the host over any side channel) and
  * passes all `world` blobs, rank-ordered, to b200rwkv_tp_connect.  After that every API call
@@ -241,26 +242,26 @@ int32_t b200rwkv_last_hidden(b200rwkv_engine*, float* out, size_t cap);
  * row-major; returns the column count (negative status on error).  Not on the product path. */
 int32_t b200rwkv_debug_read(b200rwkv_engine*, const char* name, float* out, size_t cap);
 
-/* Profiling aid.  With B200RWKV_TRACE=1 and the whole-step kernel: per-phase timer stamps of the last step
- * (out = [4 CTAs][nphase][12]).  With B200RWKV_STEP_TRACE=1 and the per-op chain: one row of 512 uint64 per launch of
- * the last captured step shape (out = [nphase = launches][512]): globaltimer stamps of CTA 0 in [0..7] (entry, past
- * griddepcontrol.wait, phase marks, exit), then {SM id, last MMA issued, exit} of every projection CTA (or {entry,
- * released, phase 1 done} of every CTA of the fused RWKV-6 front-half kernel); types[i] = 0 LN, 2 WKV, 6 front half,
- * 1000000 + weight MiB for a projection launch. */
+/* Profiling aid: raw stamp rows of the most recent b200rwkv_profile_insitu replay, one row of 512 uint64 per launch
+ * (out = [launches][512]): globaltimer stamps of CTA 0 in [0..7] (entry, past griddepcontrol.wait, phase marks, exit), then
+ * {SM id, last MMA issued, exit} of every projection CTA (or {entry, released, phase 1 done} of every CTA of the fused RWKV-6
+ * front-half kernel); types[i] = 0 LN, 2 WKV, 6 front half, 1000000 + weight MiB for a projection launch. */
 int32_t b200rwkv_debug_trace(b200rwkv_engine*, uint64_t* out, size_t cap, int32_t* types, int32_t* nphase);
 
 /* Profiling aid: one projection launch class timed in isolation over all layers. */
 int32_t b200rwkv_debug_gemm_time(b200rwkv_engine*, int32_t which, int32_t reps, float* ms_out, int64_t* bytes_out,
                                  uint64_t* trace_out);
 
-/* Profiling aid: HBM streaming micro-benchmark (plain loads vs the bulk-TMA stage ring). */
+#ifdef B200RWKV_DEBUG
+/* Debug build only (libb200rwkv_dbg.so, `python -m ai00_server_b200.build --debug`): HBM streaming and L2 prefetch
+ * micro-benchmarks (csrc/streamtest.cuh).  The debug build also honours the B200RWKV_* bring-up environment switches;
+ * the product library ignores the environment. */
 int32_t b200rwkv_debug_stream(int32_t device, int32_t kind, double gbytes, int32_t stage_bytes, int32_t nstage,
                               int32_t use_hint, int32_t consumer, int32_t split, int32_t producers, int32_t reps,
                               float* ms_out);
-
-/* Profiling aid: is an L2 prefetch issued while HBM idles still there when the next launch streams? (streamtest.cuh) */
 int32_t b200rwkv_debug_prefetch(int32_t device, double mbytes, int32_t consumers, int32_t pf_grid, int32_t skip, int32_t nblk,
                                 int32_t mode, double idle_us, int32_t reps, float* ms_out);
+#endif
 
 const char* b200rwkv_last_error(b200rwkv_engine*);
 

@@ -3,7 +3,7 @@ Rows: streamed MB, consumer CTAs, prefetched blocks per consumer (32 KB each), m
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ai00_server_b200 import capi
-L = capi.lib()
+L = capi.debug_lib()        # python -m ai00_server_b200.build --debug
 def run(mb, consumers, pf_grid, skip, nblk, mode, idle_us, reps=8):
     ms = (C.c_float * 2)()
     capi.check(L.b200rwkv_debug_prefetch(0, mb, consumers, pf_grid, skip, nblk, mode, idle_us, reps, ms))

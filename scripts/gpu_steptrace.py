@@ -1,8 +1,7 @@
-"""Timeline of one decode step of the per-op chain (B200RWKV_STEP_TRACE=1): globaltimer stamps of CTA 0 of every launch.
+"""Timeline of one graph-replayed decode step (b200rwkv_profile_insitu + b200rwkv_debug_trace): globaltimer stamps of CTA 0 of every launch.
 Rows: label, entry, past griddepcontrol.wait, ..., exit -- all in us relative to the first launch of the printed layer."""
 import ctypes as C, os, sys
 import numpy as np
-os.environ["B200RWKV_STEP_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ai00_server_b200 import capi, runtime, synth
 
@@ -14,6 +13,7 @@ slots = list(range(B))
 rng = np.random.default_rng(0)
 for i in range(8):
     m.infer_raw(slots, [1] * B, rng.integers(1, 60000, B).tolist(), [0] * B)
+m.profile_insitu(slots, rng.integers(1, 60000, B).astype(np.uint32), reps=2)      # traced replays leave their stamp rows behind
 ROW = 512
 buf = np.zeros(1024 * ROW, np.uint64); types = np.zeros(1024, np.int32); n = C.c_int32(0)
 capi.check(capi.lib().b200rwkv_debug_trace(m._h, capi.ptr(buf), buf.size, capi.ptr(types), C.byref(n)), m._h)

@@ -1,7 +1,7 @@
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ai00_server_b200 import capi
-L = capi.lib()
+L = capi.debug_lib()        # python -m ai00_server_b200.build --debug
 def run(kind, gb=4.0, stage=16384, nstage=12, hint=1, consumer=0, split=1, producers=1, reps=5):
     ms = C.c_float(0)
     capi.check(L.b200rwkv_debug_stream(0, kind, gb, stage, nstage, hint, consumer, split, producers, reps, C.byref(ms)))

@@ -20,14 +20,30 @@ def _has_gpu():
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "b200rwkv.h")).read()
-    declared = set(re.findall(r"\b(b200rwkv_[a-z0-9_]+)\s*\(", hdr))
-    declared -= {"b200rwkv_status", "b200rwkv_info", "b200rwkv_engine"}
-    assert len(declared) >= 20
+    # the debug-build section (#ifdef B200RWKV_DEBUG ... #endif) is not part of the product library
+    product_hdr = re.sub(r"#ifdef B200RWKV_DEBUG.*?#endif", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(b200rwkv_[a-z0-9_]+)\s*\(", product_hdr))
+    declared -= {"b200rwkv_status", "b200rwkv_info", "b200rwkv_engine", "b200rwkv_options"}
+    assert len(declared) >= 30
     lib = capi.lib()
     bound = {n for n, _, _ in capi.SYMBOLS}
     assert declared == bound, (declared ^ bound)
     for name in declared:
         assert getattr(lib, name) is not None
+    for name, _, _ in capi.DEBUG_SYMBOLS:            # and the product library really does not carry the debug entries
+        assert not hasattr(lib, name)
+
+
+def test_product_library_ignores_the_environment():
+    """The bring-up switches (B200RWKV_*) exist only in the debug build: every getenv in the engine sources sits inside an
+    `#ifdef B200RWKV_DEBUG` block (the CUDA runtime linked into the library reads its own CUDA_* variables)."""
+    csrc = os.path.join(ROOT, "ai00_server_b200", "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if not f.endswith((".cu", ".cuh")):
+            continue
+        src = open(os.path.join(csrc, f)).read()
+        outside = re.sub(r"#ifdef B200RWKV_DEBUG.*?#e(?:lse|ndif)", "", src, flags=re.S)
+        assert "getenv(" not in outside, f
 
 
 def test_info_from_st_host_only():
