@@ -52,6 +52,8 @@ PRESETS = {
     "tiny5": Shape(5, 2, 256, 896, V=512),
     "tiny7": Shape(7, 3, 256, 1024, V=512, Dd=32, Da=32, Dv=16, Dg=64),
     "small6": Shape(6, 4, 512, 1792, V=2048, Dm=32, Dd=64),
+    "small5": Shape(5, 3, 512, 1792, V=2048),                                   # 8 heads: shards over 8 GPUs
+    "small7": Shape(7, 3, 512, 2048, V=2048, Dd=32, Da=32, Dv=16, Dg=64),
     # BASELINE.json shapes (last row)
     "v6-1b6": Shape(6, 24, 2048, 7168, Dm=32, Dd=64),
     "v6-3b": Shape(6, 32, 2560, 8960, Dm=32, Dd=64),

@@ -43,7 +43,7 @@ def test_one_engine_object_drives_all_ranks():
     from ai00_server_b200 import capi, runtime, synth
     world = min(_ngpu(), 8)
     world = 8 if world >= 8 else (4 if world >= 4 else 2)
-    for preset in ("small6", "tiny7", "tiny5"):
+    for preset in ("small6", "small7", "small5"):
         st = synth.make_st(preset, 0)
         single = runtime.Model(st, max_batch=4, token_chunk_size=32, device=0)
         multi = runtime.Model(st, max_batch=4, token_chunk_size=32, devices=list(range(world)))

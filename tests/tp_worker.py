@@ -20,7 +20,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    for preset in sys.argv[1:] or ["small6", "tiny7", "tiny5"]:
+    for preset in sys.argv[1:] or ["small6", "small7", "small5"]:          # 8 heads each: every world size up to 8 divides them
         st = synth.make_st(preset, 0)
         m = runtime.Model(st, max_batch=4, token_chunk_size=32, device=local, rank=rank, world=world)
         tp.connect(m)
