@@ -30,14 +30,17 @@ struct MetaView {
 };
 
 // ---------------------------------------------------------------------------------------
-// "A16" activation layout: the f16 operand of every projection, stored as the UMMA canonical
-// K-major / no-swizzle layout of a 16-token tile so that (a) the k-range a GEMM stage needs is one
-// contiguous 2 KB run (one bulk TMA copy) and (b) tcgen05.mma reads it from shared memory as is:
-//   [m_tile][k8 chunk][16 token rows][8 halves]      (8 rows x 16 B = one 128-byte core matrix)
-// `kq_per_tile` = padded K / 32 (k32 blocks per tile), so K / 8 = 4 * kq_per_tile chunks.
+// "A16" activation layout: the f16 operand of every projection, stored so that (a) the slice a GEMM stage needs -- one
+// 128-wide k block of ALL token tiles of the step -- is ONE contiguous run (one bulk TMA copy of MT x 4 KB) and (b) each
+// 16-token tile of that run is the UMMA canonical K-major / no-swizzle layout tcgen05.mma reads from shared memory as is:
+//   [k block (128 k)][token tile (16 tokens)][k8 chunk 16][16 token rows][8 halves]   (8 rows x 16 B = one core matrix)
+// Every buffer holds A16_MTILES token tiles (= the largest step, 128 tokens) and K padded to whole k blocks.
 // ---------------------------------------------------------------------------------------
-__host__ __device__ inline size_t a16_index(int m, int k, int kq_per_tile) {
-    return (((size_t)(m >> 4) * (4 * kq_per_tile) + (k >> 3)) * 16 + (m & 15)) * 8 + (k & 7);
+constexpr int A16_MTILES = 8;                          // token tiles per buffer: steps of up to 128 tokens
+constexpr int A16_TILE_HALVES = 16 * 128;              // one token tile of one k block: 4 KB
+constexpr int A16_KB_HALVES = A16_MTILES * A16_TILE_HALVES;
+__host__ __device__ inline size_t a16_index(int m, int k, int /*unused*/ = 0) {
+    return ((((size_t)(k >> 7) * A16_MTILES + (m >> 4)) * 16 + ((k >> 3) & 15)) * 16 + (m & 15)) * 8 + (k & 7);
 }
 
 __device__ __forceinline__ __half f2h_sat(float v) {

@@ -413,7 +413,7 @@ struct b200rwkv_engine {
     std::unique_ptr<Group> group;             // set on rank 0 of an in-process tensor-parallel engine
     b200rwkv_info info;
     int dev = 0, rank = 0, world = 1, num_sms = 148;
-    int S = 0, chunk = 0, maxT = 64, precision = 0;
+    int S = 0, chunk = 0, maxT = 16 * A16_MTILES, precision = 0;      // steps of up to 128 tokens
     int L = 0, C = 0, F = 0, V = 0, H = 0, N = 64, Cl = 0, Hl = 0, Fl = 0, Vl = 0;
     bool use_graph = true, use_pdl = true;
     int split_att = 1, split_ffn = 1;
@@ -656,7 +656,7 @@ A16Buf b200rwkv_engine::a16_alloc(int K, int nmat) {
     A16Buf b;
     const int Kp = rup(K, GEMM_BK);          // whole 128-wide k blocks, zero padded
     b.kq = Kp / 32;
-    b.halves_per_matrix = (size_t)(maxT / 16) * b.kq * 512;
+    b.halves_per_matrix = (size_t)(Kp / GEMM_BK) * A16_KB_HALVES;
     b.p = (__half*)dalloc(b.halves_per_matrix * 2 * nmat, true);
     return b;
 }
@@ -778,7 +778,8 @@ void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, P
             else launch_k(gemm_kernel<1, 2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             break;
         case 2: launch_k(gemm_kernel<2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<2>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
-        default: launch_k(gemm_kernel<4>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<4>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
+        case 4: launch_k(gemm_kernel<4>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<4>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
+        default: launch_k(gemm_kernel<8>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<8>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
     }
 }
 
@@ -817,6 +818,16 @@ void b200rwkv_engine::build(const StFile& st) {
     CK(cudaFuncSetAttribute(gemm_kernel<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 2>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<4>::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<8>::SMEM_BYTES));
+    {   // prefill steps of up to 128 tokens: per-token decay rows of a slot live in dynamic shared memory
+        const int wkv_smem_max = 96 * 1024;
+        CK(cudaFuncSetAttribute(wkv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, wkv_smem_max));
+        CK(cudaFuncSetAttribute(wkv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, wkv_smem_max));
+        CK(cudaFuncSetAttribute(wkv_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, wkv_smem_max));
+        CK(cudaFuncSetAttribute(wkv_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wkv_smem_max));
+        CK(cudaFuncSetAttribute(wkv_kernel<6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wkv_smem_max));
+        CK(cudaFuncSetAttribute(wkv_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wkv_smem_max));
+    }
     if (precision == 1) split_act = true;         // f32-activation mode (web-rwkv `Bundle::<f32>`): no activation is rounded to f16
     if (const char* v = dbg_env("B200RWKV_PREFETCH_BLOCKS")) prefetch_blocks = std::max(0, atoi(v));
     if (const char* v = dbg_env("B200RWKV_FUSED_PRE")) fused_pre = atoi(v) != 0;
@@ -910,7 +921,8 @@ void b200rwkv_engine::build(const StFile& st) {
                        const float* bias, int a_koff = 0, int a_mat = 0) {
         SegDesc d;
         d.t = &t; d.n0 = n0; d.N = Nn; d.k0 = k0; d.K = K;
-        d.proto.A = ab.p + (size_t)a_mat * ab.halves_per_matrix + (size_t)(a_koff / 8) * 128; d.proto.a_k8 = ab.kq * 4;
+        REQUIRE(a_koff % GEMM_BK == 0, B200RWKV_ERR_INVALID, "internal: split-K slices start on k-block boundaries");
+        d.proto.A = ab.p + (size_t)a_mat * ab.halves_per_matrix + (size_t)(a_koff / GEMM_BK) * A16_KB_HALVES; d.proto.a_k8 = ab.kq * 4;
         d.proto.out_mode = OUT_F32; d.proto.act = act; d.proto.bias = bias; d.proto.out = out; d.proto.ldo = ldo;
         return d;
     };
@@ -1360,7 +1372,7 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
     if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
 }
 
-static inline int mt_bucket(int rows) { return rows <= 16 ? 1 : (rows <= 32 ? 2 : 4); }
+static inline int mt_bucket(int rows) { return rows <= 16 ? 1 : (rows <= 32 ? 2 : (rows <= 64 ? 4 : 8)); }
 
 // last logits row of every slot of this step -> keep[slot] (rank 0 gathers the vocabulary shards); see sample.cuh
 void b200rwkv_engine::enqueue_keep(cudaStream_t s, int MTR) {
@@ -2421,7 +2433,7 @@ int32_t b200rwkv_op_wkv(int32_t device, int32_t version, int32_t T, int32_t H, c
         p.k_k = up(k_k, Cc, 0.f); p.k_a = up(k_a, Cc, 0.f); p.r_k = up(r_k, Cc, 0.f);
     }
     const int kq = rup(Cc, GEMM_BK) / 32;
-    const size_t halves = (size_t)(maxT / 16) * kq * 512;
+    const size_t halves = (size_t)(rup(Cc, GEMM_BK) / GEMM_BK) * A16_KB_HALVES;
     keep.push_back(new DevTmp(halves * 2));
     p.out = (__half*)keep.back()->p;
     p.kq_tile = kq;

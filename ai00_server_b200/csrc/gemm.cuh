@@ -15,7 +15,7 @@
 //   * weights are re-tiled ONCE at load into 32 KB stage blocks (128 output rows x 128 k) already
 //     in the UMMA canonical K-major / no-swizzle shared-memory layout, so a pipeline stage is ONE
 //     contiguous 1-D bulk TMA copy (cp.async.bulk -> UBLKCP) that the tensor core reads in place;
-//     activations use the matching A16 layout (common.cuh): one 4 KB bulk copy per stage (the
+//     activations use the matching A16 layout (common.cuh): one bulk copy of MT x 4 KB per stage (the
 //     issue rate of bulk copies, ~0.3 us each per thread, is what sizes the stage);
 //   * warp roles: one TMA producer lane drives a 4-6 stage mbarrier ring; one MMA lane consumes
 //     it (tcgen05.commit releases each slot when its MMAs retire); four epilogue warps drain the
@@ -56,8 +56,8 @@ enum OutMode : int {
 };
 
 struct GemmSeg {
-    const __half* A;      // A16 activations for this segment (already offset to the segment's first k)
-    int a_k8;             // 16-byte k chunks per 16-token tile of the A16 buffer (its padded K / 8)
+    const __half* A;      // A16 activations for this segment (already offset to the segment's first k block)
+    int a_k8;             // (unused)
     int KB;               // 128-wide k blocks (K padded up)
     int tiles;            // 128-row output tiles (N padded up)
     int N;                // valid output columns
@@ -444,10 +444,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, RING == 1 ? 2 : 1) gemm_kernel(c
                     mbar_expect_tx(fb, Cfg::STAGE_BYTES);
                     bulk_g2s_hint(st, p.W + (size_t)b * GEMM_WBYTES, GEMM_WBYTES, fb, pol_w);
                 }
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-                    bulk_g2s_hint(st + GEMM_WBYTES + mt * GEMM_ABYTES,
-                                  sg->A + ((size_t)mt * sg->a_k8 + GEMM_K8 * kb) * 128, GEMM_ABYTES, fb, pol_a);
+                // the k block's slice of all MT token tiles is one contiguous run of the A16 layout (common.cuh)
+                bulk_g2s_hint(st + GEMM_WBYTES, sg->A + (size_t)kb * A16_KB_HALVES, MT * GEMM_ABYTES, fb, pol_a);
                 if (++stage == Cfg::NSTAGE) { stage = 0; ephase ^= 1; }
                 if (++kb == sg->KB) kb = 0;
                 if (--blocks_left_in_seg == 0 && b + 1 < b1) {

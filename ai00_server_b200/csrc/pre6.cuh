@@ -332,13 +332,13 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
         // split operands: the lo halves of the 16 tokens are the second 16-token tile of the same A16 buffer
 #pragma unroll
         for (int sp = 0; sp < (SPLIT ? 2 : 1); ++sp) {
-            const __half* xa = p.ln.mix_out[0] + (sp ? a16_index(16, 0, p.ln.kq_tile) : (size_t)0);      // A16 [16][C] tile
+            const __half* xa = p.ln.mix_out[0];      // A16: token tile 0 (hi) / 1 (lo) of every k block
             uint32_t af[PRE_KSW][4];
 #pragma unroll
             for (int i = 0; i < PRE_KSW; ++i) {
                 const int kstep = warp + 8 * i;
-                const int k = (int)rank * Cs + kstep * 16;
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(xa + ((size_t)(k >> 3) * 16 + grp) * 8 + tig * 2);
+                const int k = (int)rank * Cs + kstep * 16;     // a 16-wide k step never straddles a 128-wide k block
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(xa + a16_index(16 * sp + grp, k + tig * 2));
                 const bool ok = kstep < ksteps;
                 af[i][0] = ok ? __ldcg(src) : 0u;               // (t = grp,     k lo)
                 af[i][1] = ok ? __ldcg(src + 32) : 0u;          // (t = grp + 8, k lo)   +64 halves
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
                     dst[a16_index(t, nn, p.lora_kq)] = hi;
                     dst[a16_index(t + 16, nn, p.lora_kq)] = lo;
                 } else {
-                    dst[((size_t)(nn >> 3) * 16 + t) * 8 + (nn & 7)] = f2h_sat(apply_act(s, ACT_TANH));
+                    dst[a16_index(t, nn)] = f2h_sat(apply_act(s, ACT_TANH));
                 }
             }
         }

@@ -168,7 +168,8 @@ def prefill_main(args):
     steps, warm = max(1, min(args.steps, 4)), max(3, args.warmup if args.warmup < 8 else 3)
     metric = f"prefill tokens/s {MODEL_NAMES.get(preset, preset)} fp16 {B}x{Tn}-token inputs (embeddings route)"
     st = synth.make_st(shape, 0)
-    model = runtime.Model(st, max_batch=B, token_chunk_size=64, device=0)
+    PASS = 128                                              # tokens per weight pass (the engine's largest step)
+    model = runtime.Model(st, max_batch=B, token_chunk_size=PASS, device=0)
     slots = list(range(B))
     rng = np.random.default_rng(1234)
     toks = rng.integers(1, min(shape.V, 65530), size=(B, Tn), dtype=np.int64)
@@ -221,27 +222,28 @@ def prefill_main(args):
     model.infer_raw(slots[:nb], [nt] * nb, toks[:nb, :nt].reshape(-1).tolist(), [capi.OPTION_NONE] * nb)
     errs = [float(np.abs(model.state.back(i) - cst[i]).max() / np.abs(cst[i]).max()) for i in range(nb)]
     peaks, peak_src = read_peaks()
-    n_pass = -(-ntok // 64)
+    n_pass = -(-ntok // PASS)
     wbytes = 2 * (synth.num_params(shape) - shape.V * shape.C)              # every pass streams all weights but the embedding
-    pass_bytes = wbytes + 64 * 2 * shape.L * (shape.H * 64 * 64 + 2 * shape.C) * 4
+    pass_bytes = wbytes + PASS * 2 * shape.L * (shape.H * 64 * 64 + 2 * shape.C) * 4
     flops = 2.0 * (synth.num_params(shape) - 2 * shape.V * shape.C) * ntok  # no head: the route needs no logits
     line = {"metric": metric, "value": ntok / dt, "unit": "tokens/s", "n_gpus": 1, "steps": steps, "warmup": warm,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"{preset} prefill, {B} sequences x {Tn} tokens, no logits, final state of every sequence returned",
-                       "preset": preset, "seqs": B, "seq_len": Tn, "tokens_per_pass": 64,
-                       "l2": "inputs larger than L2 (5.9 GB of weights streamed per 64-token pass), no flush"},
+                       "preset": preset, "seqs": B, "seq_len": Tn, "tokens_per_pass": PASS,
+                       "l2": f"inputs larger than L2 (5.9 GB of weights streamed per {PASS}-token pass), no flush"},
             "clocks": clocks,
             "e2e": {"value": ntok / de, "unit": "tokens/s", "ms_per_step": de * 1e3, "h2d_bytes_per_step": int(ntok * 4 + n_pass * 1800),
                     "d2h_bytes_per_step": int(state_buf.nbytes),
                     "api": "b200rwkv_infer (host token ids, OPTION_NONE) + b200rwkv_state_back of every slot (the embedding, run.rs:984-989)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "gemm_kernel (64-token passes: every pass streams all projection weights)",
+            "roofline": {"bound": "hbm", "kernel": f"gemm_kernel<8> ({PASS}-token passes: every pass streams all projection weights once)",
                          "achieved": n_pass * pass_bytes / dt / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": n_pass * pass_bytes / dt / 1e9 / peaks["hbm_gbs"], "traffic": None,
                          "peak_source": f"MEASURED_PEAKS.json ({peak_src})", "passes": n_pass, "bytes_per_pass": int(pass_bytes),
                          "tensor_tflops_achieved": flops / dt / 1e12, "tensor_tflops_peak_sustained": peaks.get("bf16_tflops_sustained"),
-                         "note": "this route is tensor-bound only with >= 256 tokens per weight pass; at 64 tokens per pass it is bound "
-                                 "by re-streaming the weights (DESIGN.md: chunked prefill is the next step)"},
+                         "note": f"the route turns tensor-bound at >= 280 FLOP/B = ~300 tokens per weight pass; at {PASS} tokens per pass "
+                                 "(shared memory: 32 KB weights + 32 KB tokens per stage, TMEM: 256 of 512 columns) it is still bound by "
+                                 "streaming the weights, which is what `achieved` measures"},
             "cpu_baseline": {"value": nb * nt / cdt, "unit": "tokens/s", "cores": rc.num_threads(), "kind": "port",
                              "sample": f"first {nt} tokens of the first {nb} sequences, C/OpenMP oracle (token by token)"},
             "state_checksum": {"sum": checksum[0], "abs_sum": checksum[1]},
@@ -373,8 +375,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = {"value": BATCH * e2e_steps / e2e_s, "unit": "tokens/s", "ms_per_step": e2e_s / e2e_steps * 1e3,
-           "h2d_bytes_per_step": int((8 + 6 * 64 + 3 * BATCH) * 4), "d2h_bytes_per_step": int(out.nbytes),
+           "h2d_bytes_per_step": int((8 + 6 * 128 + 3 * BATCH) * 4), "d2h_bytes_per_step": int(out.nbytes),
            "api": "runtime.Model.infer_raw -> b200rwkv_infer (host token ids in, host f32 logits out, wall clock)"}
+
+    # ---- e2e with the GPU sampling front half: logits stay in HBM, <= 128 (id, prob) pairs per slot come back ----
+    ids = probs = None
+    for i in range(args.warmup):
+        model.infer_raw(slots, [1] * BATCH, dec2[:, i].tolist(), [0] * BATCH, keep_on_device=True)
+        if rank == 0:
+            ids, probs = model.sample_topk(slots, top_k=128)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        model.infer_raw(slots, [1] * BATCH, dec2[:, args.warmup + i].tolist(), [0] * BATCH, keep_on_device=True)
+        if rank == 0:
+            ids, probs = model.sample_topk(slots, top_k=128)
+    barrier()
+    e2s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2s = float(t.item())
+    e2e["sampled"] = {"value": BATCH * e2e_steps / e2s, "unit": "tokens/s", "ms_per_step": e2s / e2e_steps * 1e3,
+                      "d2h_bytes_per_step": int(BATCH * 128 * 8),
+                      "api": "b200rwkv_infer(logits_out = NULL) + b200rwkv_sample_topk(top_k = 128): the reference's nucleus default"}
 
     # ---- roofline of the dominant kernel (projection GEMM); SPMD under tensor parallelism ----
     # In-situ windows of a graph-replayed step (globaltimer stamps written by the kernels: [wait released, last CTA exit]);

@@ -125,7 +125,8 @@ int32_t b200rwkv_get_info(b200rwkv_engine*, b200rwkv_info* out);
 /* Replaces `Runtime::infer(RnnInput)` — crates/ai00-core/src/run.rs:1143 — for one
  * `RnnInput`: a ragged batch of `nslot` entries; entry i feeds `ntok[i]` tokens
  * (tokens + sum(ntok[0..i])) to state slot `slot[i]` with RnnOption `option[i]`.
- * All tokens are consumed (internally in chunks of at most token_chunk_size, the policy
+ * All tokens are consumed (internally in steps of at most min(token_chunk_size, 128) tokens shared evenly over the
+ * entries, the policy
  * web-rwkv applies across calls at run.rs:1134-1145).  Logits rows (num_vocab f32 each) are
  * written contiguously to `logits_out` in entry order: 1 row for LAST (0 if ntok[i]==0),
  * ntok[i] rows for FULL, none for NONE; rows_out[i] receives the row count of entry i
@@ -234,7 +235,7 @@ int32_t b200rwkv_launch_count(b200rwkv_engine*, int64_t* total);
 /* The residual stream after the last layer, one [num_emb] f32 row per token -- the hidden state the documented embeddings
  * route returns (reference docs/doc-api/openai.md:376-437).  After b200rwkv_keep_hidden(e, 1) every infer call records the
  * rows of ALL its tokens (entry order, like the token array); without it only the rows of the call's last internal step
- * (<= 64 tokens) are available.  b200rwkv_last_hidden returns the number of rows written (negative status on error). */
+ * (<= 128 tokens) are available.  b200rwkv_last_hidden returns the number of rows written (negative status on error). */
 int32_t b200rwkv_keep_hidden(b200rwkv_engine*, int32_t enable);
 int32_t b200rwkv_last_hidden(b200rwkv_engine*, float* out, size_t cap);
 

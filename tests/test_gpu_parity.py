@@ -411,3 +411,24 @@ def test_full_rows_stay_in_entry_order_when_steps_interleave_slots(models):
     for s, r in enumerate(runs):
         want, _ = orc.run(r, orc.state_init(), full=(s != 1))
         assert rel_err(rows[s], want) <= REL_TOL and (rows[s].argmax(1) == np.atleast_2d(want).argmax(1)).all()
+
+
+@pytest.mark.parametrize("preset", ["tiny6", "tiny7", "tiny5"])
+def test_prefill_steps_of_128_tokens(models, preset):
+    """token_chunk_size 128: prefill runs as 128-token steps (eight 16-token operand tiles per projection stage); same logits
+    and state as the oracle's token-by-token run, for one long prompt and for several prompts sharing the steps."""
+    m, orc, _ = models(preset, chunk=128)
+    rng = np.random.default_rng(51)
+    long_run = rng.integers(1, 500, size=300).tolist()
+    m.state.load(m.state.init(), 0)
+    got = feed(m, 0, long_run)
+    want, want_st = orc.run(long_run, orc.state_init())
+    assert rel_err(got, want) <= REL_TOL and got.argmax() == want.argmax()
+    assert rel_err(m.state.back(0), want_st) <= 2 * REL_TOL
+    runs = [rng.integers(1, 500, size=n).tolist() for n in (70, 130, 9, 41)]
+    for s in range(4):
+        m.state.load(m.state.init(), s)
+    rows = m.infer_raw([0, 1, 2, 3], [len(r) for r in runs], sum(runs, []), [capi.OPTION_LAST] * 4)
+    for s, r in enumerate(runs):
+        want, _ = orc.run(r, orc.state_init())
+        assert rel_err(rows[s], want) <= REL_TOL and rows[s].argmax() == want.argmax()
