@@ -231,9 +231,9 @@ __device__ __forceinline__ void wkv_slot(const WkvParams& p, const int h, const 
 // Shape: 64 heads x 16 slots = 1024 CTAs must be ONE wave (measured: with 256 threads x 64 registers only 592 fit and the
 // second wave doubled the kernel), i.e. <= 72 registers at 7 CTAs per SM with half of them holding state.
 // A decode step is a latency chain, not bandwidth (16 KB of state per CTA), so everything no kernel of this step writes --
-// the decay-LoRA slice, ln_x, time_first, the step metadata -- is staged BEFORE griddepcontrol.wait, and after it one
-// batch of loads brings the state patch, the head's r/k/v/g(/w/a/nu) rows of up to WKV_STAGE_TOK tokens and the
-// decay-LoRA inputs; longer slots (prefill chunks) read per token instead.
+// the decay-LoRA slice, ln_x, time_first, the step metadata, and the state patch itself -- is requested BEFORE
+// griddepcontrol.wait, and after it one batch of loads brings the head's r/k/v/g(/w/a/nu) rows of up to WKV_STAGE_TOK
+// tokens and the decay-LoRA inputs; longer slots (prefill chunks) read per token instead.
 constexpr int WKV_SA_THREADS = 128;
 constexpr int WKV_SA_KC = 8;
 constexpr int WKV_STAGE_TOK = 4;
@@ -299,20 +299,25 @@ __global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_con
     const int slot = live ? p.meta.slot_id()[si] : 0;
     const int t0 = live ? p.meta.slot_start()[si] : 0;
     const int nt = live ? p.meta.slot_count()[si] : 0;
+    // The state patch is requested BEFORE the wait as well: no kernel of this step but this one touches this layer's WKV
+    // state, and CTAs that become resident while the slowest CTAs of the preceding projection are still finishing (its
+    // tail skews by several microseconds) spend that time pulling their 16 KB from HBM instead of idling.
+    float* M = p.state + ((size_t)slot * p.H + h) * (WKV_N * WKV_N);
+    float m[4][KC];
+    if (live) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int q = 0; q < KC / 4; ++q) {
+                const float4 v4 = __ldcs(reinterpret_cast<const float4*>(M + (ig * 4 + e) * WKV_N + j4 * KC + q * 4));
+                m[e][q * 4] = v4.x; m[e][q * 4 + 1] = v4.y; m[e][q * 4 + 2] = v4.z; m[e][q * 4 + 3] = v4.w;
+            }
+    }
     pdl_wait();
     trace_stamp(p.trace, 1);
     if (!live) return;
 
-    // ---- one batch of loads: state patch, staged rows, decay-LoRA inputs ----
-    float* M = p.state + ((size_t)slot * p.H + h) * (WKV_N * WKV_N);
-    float m[4][KC];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int q = 0; q < KC / 4; ++q) {
-            const float4 v4 = __ldcs(reinterpret_cast<const float4*>(M + (ig * 4 + e) * WKV_N + j4 * KC + q * 4));
-            m[e][q * 4] = v4.x; m[e][q * 4 + 1] = v4.y; m[e][q * 4 + 2] = v4.z; m[e][q * 4 + 3] = v4.w;
-        }
+    // ---- one batch of loads: staged rows, decay-LoRA inputs ----
     const bool staged = nt <= WKV_STAGE_TOK;
     if (staged) {
         constexpr int UMAX = WKV_STAGE_ARRAYS * WKV_STAGE_TOK * WKV_N / NT;      // 14
