@@ -1501,7 +1501,9 @@ void b200rwkv_engine::infer(int nslot, const int32_t* slot, const int32_t* ntok,
         if (n_active == 0) break;
         std::vector<int> s_entry, s_slots, s_counts, s_out;
         std::vector<const uint32_t*> s_toks;
-        const int quota = std::max(1, step_cap / n_active);
+        // at least WKV_STAGE_TOK tokens per slot and step while prompts are long: a WKV CTA then loads and stores its 16 KB
+        // of state once per four tokens (staged path) and a step touches a quarter of the slots' states
+        const int quota = std::max(WKV_STAGE_TOK, step_cap / n_active);
         int used = 0;
         for (int i = 0; i < nslot && used < step_cap; ++i) {
             const int remain = ntok[i] - pos[i];

@@ -241,11 +241,12 @@ constexpr int WKV_STAGE_ARRAYS = 7;      // r, k, v, g, w, a, nu
 
 __host__ __device__ inline int wkv_stage_arrays(int ver, bool fold) { return ver == 7 ? 7 : ((ver == 6 && !fold) ? 5 : 4); }
 
-// dynamic shared memory: [fold only: [Dd][64] halves (k-major slice of time_decay_w2) | [max tokens][64] floats (decays) |
+// dynamic shared memory: [fold only: [Dd][64] halves (k-major slice of time_decay_w2) | [WKV_STAGE_TOK][64] floats (decays) |
 // [WKV_STAGE_TOK][Dd] halves | [2][64] floats] | staged rows [arrays][WKV_STAGE_TOK][64] floats | statics [3][64] floats
 __host__ __device__ inline size_t wkv_smem_bytes(int ver, bool fold, int Dd, int max_tokens, bool split = false) {
     size_t b = 0;
-    if (fold) b += (size_t)WKV_N * Dd * 2 + (size_t)max_tokens * WKV_N * 4 + ((((size_t)WKV_STAGE_TOK * Dd * 2 * (split ? 2 : 1)) + 15) & ~(size_t)15) + 2 * WKV_N * 4;
+    (void)max_tokens;      // decay rows are kept for the staged tokens only; longer runs fold one token at a time
+    if (fold) b += (size_t)WKV_N * Dd * 2 + (size_t)WKV_STAGE_TOK * WKV_N * 4 + ((((size_t)WKV_STAGE_TOK * Dd * 2 * (split ? 2 : 1)) + 15) & ~(size_t)15) + 2 * WKV_N * 4;
     b += (size_t)wkv_stage_arrays(ver, fold) * WKV_STAGE_TOK * WKV_N * 4 + 3 * WKV_N * 4 + 64;
     return b;
 }
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_con
     float* part = nullptr;
     if (fold) {
         wl = reinterpret_cast<float*>(dyn + (size_t)WKV_N * Dd * 2);
-        ds = reinterpret_cast<__half*>(wl + (size_t)max_tokens * WKV_N);
+        ds = reinterpret_cast<__half*>(wl + (size_t)WKV_STAGE_TOK * WKV_N);
         part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ds) + ((((size_t)WKV_STAGE_TOK * Dd * 2 * (SPLIT ? 2 : 1)) + 15) & ~(size_t)15));
         dyn = reinterpret_cast<uint8_t*>(part + 2 * WKV_N);
     }
@@ -358,41 +359,49 @@ __global__ void __launch_bounds__(WKV_SA_THREADS, 7) wkv_kernel(const __grid_con
             }
     }
 
-    const float* w_local = nullptr;
-    if (fold) {
-        // w[t][c] = exp(-exp(time_decay[c] + sum_k Wd2[c][k] * tanh(Wd1 xw)[t][k]))   
+    // w[t][c] = exp(-exp(time_decay[c] + sum_k Wd2[c][k] * tanh(Wd1 xw)[t][k]))   (SURVEY.md App. A), for the token whose
+    // decay-LoRA input sits at `dt` (hi) / `dt + WKV_STAGE_TOK * Dd` (lo halves of split operands), into wl[slot_tok][64]
+    auto fold_token = [&](const __half* dt, const int slot_tok) {
         const int c = tid & (WKV_N - 1), qk = tid >> 6;
         const int kq0 = qk * (Dd >> 1), kq1 = kq0 + (Dd >> 1);
+        float acc0 = 0.f, acc1 = 0.f;
+        if (SPLIT) {
+            const __half* dl = dt + WKV_STAGE_TOK * Dd;
+            for (int k = kq0; k < kq1; k += 2) {
+                acc0 = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(dt[k]) + __half2float(dl[k]), acc0);
+                acc1 = fmaf(__half2float(wt[(k + 1) * WKV_N + c]), __half2float(dt[k + 1]) + __half2float(dl[k + 1]), acc1);
+            }
+        } else {
+            for (int k = kq0; k < kq1; k += 2) {
+                acc0 = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(dt[k]), acc0);
+                acc1 = fmaf(__half2float(wt[(k + 1) * WKV_N + c]), __half2float(dt[k + 1]), acc1);
+            }
+        }
+        part[qk * WKV_N + c] = acc0 + acc1;
+        __syncthreads();
+        if (tid < WKV_N) wl[slot_tok * WKV_N + c] = expf(-expf(bias + (part[c] + part[WKV_N + c])));
+    };
+    if (staged || !fold) {
+        if (fold)
+            for (int tt = 0; tt < nt; ++tt) {
+                __syncthreads();
+                fold_token(ds + tt * Dd, tt);
+            }
+        __syncthreads();
+        wkv_slot<VER, KC, SPLIT>(p, h, t0, nt, m, sm, fold ? wl : nullptr, 0, staged ? pre_s : nullptr, WKV_STAGE_TOK * WKV_N, statics);
+    } else {
+        // long run of one slot (prefill chunk): token by token, the decay row of one token at a time
         for (int tt = 0; tt < nt; ++tt) {
             __syncthreads();
-            const __half* dt = staged ? ds + tt * Dd : ds;
-            if (!staged) {
-                for (int k = tid; k < Dd; k += NT) ds[k] = p.d1[a16_index(t0 + tt, k, p.d1_kq)];
-                if (SPLIT)
-                    for (int k = tid; k < Dd; k += NT) ds[WKV_STAGE_TOK * Dd + k] = p.d1[a16_index(t0 + tt + 16, k, p.d1_kq)];
-                __syncthreads();
-            }
-            float acc0 = 0.f, acc1 = 0.f;
-            if (SPLIT) {
-                const __half* dl = dt + WKV_STAGE_TOK * Dd;
-                for (int k = kq0; k < kq1; k += 2) {
-                    acc0 = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(dt[k]) + __half2float(dl[k]), acc0);
-                    acc1 = fmaf(__half2float(wt[(k + 1) * WKV_N + c]), __half2float(dt[k + 1]) + __half2float(dl[k + 1]), acc1);
-                }
-            } else {
-                for (int k = kq0; k < kq1; k += 2) {
-                    acc0 = fmaf(__half2float(wt[k * WKV_N + c]), __half2float(dt[k]), acc0);
-                    acc1 = fmaf(__half2float(wt[(k + 1) * WKV_N + c]), __half2float(dt[k + 1]), acc1);
-                }
-            }
-            part[qk * WKV_N + c] = acc0 + acc1;
+            for (int k = tid; k < Dd; k += NT) ds[k] = p.d1[a16_index(t0 + tt, k, p.d1_kq)];
+            if (SPLIT)
+                for (int k = tid; k < Dd; k += NT) ds[WKV_STAGE_TOK * Dd + k] = p.d1[a16_index(t0 + tt + 16, k, p.d1_kq)];
             __syncthreads();
-            if (tid < WKV_N) wl[tt * WKV_N + c] = expf(-expf(bias + (part[c] + part[WKV_N + c])));
+            fold_token(ds, 0);
+            __syncthreads();
+            wkv_slot<VER, KC, SPLIT>(p, h, t0 + tt, 1, m, sm, wl, 0, nullptr, WKV_STAGE_TOK * WKV_N, statics);
         }
-        w_local = wl;
     }
-    __syncthreads();
-    wkv_slot<VER, KC, SPLIT>(p, h, t0, nt, m, sm, w_local, 0, staged ? pre_s : nullptr, WKV_STAGE_TOK * WKV_N, statics);
 #pragma unroll
     for (int e = 0; e < 4; ++e)
 #pragma unroll

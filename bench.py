@@ -221,6 +221,19 @@ def prefill_main(args):
     reset()
     model.infer_raw(slots[:nb], [nt] * nb, toks[:nb, :nt].reshape(-1).tolist(), [capi.OPTION_NONE] * nb)
     errs = [float(np.abs(model.state.back(i) - cst[i]).max() / np.abs(cst[i]).max()) for i in range(nb)]
+    # where a pass goes: in-situ windows of one 128-slot x 1-token step (the shape every prefill pass has here)
+    breakdown = None
+    try:
+        wins, step_us = model.profile_insitu(slots[:PASS], toks[:PASS, 0].astype(np.uint32), reps=3)
+        agg = {}
+        for wdw in wins:
+            ty = wdw["type"]
+            name = "gemm" if ty >= 1000000 else {0: "ln_mix", 2: "wkv", 6: "front_half"}.get(ty, "ln_mix")
+            a = agg.setdefault(name, [0.0, 0])
+            a[0] += wdw["end_us"] - wdw["start_us"]; a[1] += 1
+        breakdown = {"step_us": step_us, "class_us": {k: v[0] for k, v in agg.items()}, "class_launches": {k: v[1] for k, v in agg.items()}}
+    except Exception as ex:                                  # profiling is evidence, not the measurement
+        breakdown = {"error": str(ex)}
     peaks, peak_src = read_peaks()
     n_pass = -(-ntok // PASS)
     wbytes = 2 * (synth.num_params(shape) - shape.V * shape.C)              # every pass streams all weights but the embedding
@@ -246,6 +259,7 @@ def prefill_main(args):
                                  "streaming the weights, which is what `achieved` measures"},
             "cpu_baseline": {"value": nb * nt / cdt, "unit": "tokens/s", "cores": rc.num_threads(), "kind": "port",
                              "sample": f"first {nt} tokens of the first {nb} sequences, C/OpenMP oracle (token by token)"},
+            "pass_breakdown": breakdown,
             "state_checksum": {"sum": checksum[0], "abs_sum": checksum[1]},
             "parity_check": {"what": f"final state of the first {nb} sequences after {nt} tokens vs the C oracle (f16 contract), max rel",
                              "max_rel_err": max(errs)}}

@@ -13,7 +13,7 @@ tail -n 1 $O/bench_n1.log | cut -c1-2500
 run bench_cfg2_v6_3b_b1 600 python bench.py --preset v6-3b --batch 1
 run bench_cfg4_v7_2b9_b8 600 python bench.py --preset v7-2b9 --batch 8
 B200RWKV_BENCH_CPU_STEPS=0 run bench_exact 600 python bench.py --exact --steps 64 --warmup 4
-run bench_prefill 900 python bench.py --mode prefill
+run bench_prefill 900 python bench.py --mode prefill --steps 1
 python - <<'PY'
 import json
 for n in ("bench_cfg2_v6_3b_b1", "bench_cfg4_v7_2b9_b8", "bench_exact", "bench_prefill"):
@@ -32,9 +32,9 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c
    --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 > $O/ncu_list.log 2>&1
 echo "rc=$?"; wc -l $O/launches.csv
 echo "== ncu full: one layer + the head (prefetch chain off needs the debug build; default build: traffic includes the prefetch)"
-timeout 900 ncu --set full --clock-control none --import-source on -k "$K" -s 463 -c 7 \
+timeout 900 ncu --set full --clock-control none --import-source on -k "$K" -s 513 -c 7 \
    -o $O/prof_layer -f python bench.py --steps 2 --warmup 3 > $O/ncu_full.log 2>&1
 echo "rc=$?"; ls -la $O/prof_layer.ncu-rep
-timeout 900 ncu --set full --clock-control none -k "regex:gemm_kernel" -s 1161 -c 1 \
+timeout 900 ncu --set full --clock-control none -k "regex:gemm_kernel" -s 386 -c 1 \
    -o $O/prof_head -f python bench.py --steps 2 --warmup 3 > $O/ncu_head.log 2>&1
 echo "rc=$?"; ls -la $O/prof_head.ncu-rep

@@ -58,9 +58,11 @@ def test_logits_match_oracle(models, preset):
     assert got.shape == want.shape
     assert rel_err(got, want) <= REL_TOL
     assert (got.argmax(1) == want.argmax(1)).all()
-    # the f32 activation contract is the other face of the tolerance budget
+    # against the pure-f32 contract the distance is what rounding the operands to f16 costs (the oracle's two contracts are
+    # 3e-4 .. 1e-3 apart on these models); the engine's f32-activation mode is held to 1e-4 in
+    # test_f32_activation_mode_tracks_the_f32_oracle
     want32, _ = O.Oracle(O.parse_st(st), "f32").run(toks, orc.state_init(), full=True)
-    assert rel_err(got, want32) <= REL_TOL
+    assert rel_err(got, want32) <= 2 * REL_TOL
     assert (got.argmax(1) == want32.argmax(1)).all()
     # state after the run, through State::back, in the web-rwkv layout
     back = m.state.back(0)
