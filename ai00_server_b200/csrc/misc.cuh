@@ -108,6 +108,9 @@ __device__ __forceinline__ void tp_barrier(const TpBar& b, const int lane) {
     __threadfence_system();
 }
 __global__ void tp_barrier_kernel(const TpBar b) {
+    // let the consumer (LN / front-half kernel) become resident and stage its static operands now: without this trigger it
+    // is launched only when this kernel exits, and its launch + staging latency lands on every rendezvous
+    pdl_launch_dependents();
     pdl_wait();
     tp_barrier(b, threadIdx.x);
 }
