@@ -31,16 +31,19 @@ struct MetaView {
 
 // ---------------------------------------------------------------------------------------
 // "A16" activation layout: the f16 operand of every projection, stored so that (a) the slice a GEMM stage needs -- one
-// 128-wide k block of ALL token tiles of the step -- is ONE contiguous run (one bulk TMA copy of MT x 4 KB) and (b) each
-// 16-token tile of that run is the UMMA canonical K-major / no-swizzle layout tcgen05.mma reads from shared memory as is:
-//   [k block (128 k)][token tile (16 tokens)][k8 chunk 16][16 token rows][8 halves]   (8 rows x 16 B = one core matrix)
-// Every buffer holds A16_MTILES token tiles (= the largest step, 128 tokens) and K padded to whole k blocks.
+// 128-wide k block of ALL tokens of the step -- is ONE contiguous run (one bulk TMA copy) and (b) that run IS the UMMA
+// canonical K-major / no-swizzle operand of `th` token rows, which ONE tcgen05.mma with N = th consumes:
+//   [k block (128 k)][k8 chunk 16][th token rows][8 halves]      (8 rows x 16 B = one 128-byte core matrix)
+// th = 16 x (token tiles of the step) = 16 / 32 / 64 / 128; a step's producers and consumers agree on it (the engine passes
+// it to every launch).  Measured (profiles/r02_findings.md §8): a tcgen05.mma with N = 16 costs ~80 cycles whatever N is, so
+// eight N = 16 MMAs per k step (128-token steps) made the projections MMA-bound; one N = 128 MMA does not.
+// Split operands (precision 1): th = 32, rows 0-15 hold the hi halves of the 16 tokens, rows 16-31 the lo halves.
+// Every buffer reserves 128 token rows per k block and K padded to whole k blocks (padding k is multiplied by zero weights).
 // ---------------------------------------------------------------------------------------
-constexpr int A16_MTILES = 8;                          // token tiles per buffer: steps of up to 128 tokens
-constexpr int A16_TILE_HALVES = 16 * 128;              // one token tile of one k block: 4 KB
-constexpr int A16_KB_HALVES = A16_MTILES * A16_TILE_HALVES;
-__host__ __device__ inline size_t a16_index(int m, int k, int /*unused*/ = 0) {
-    return ((((size_t)(k >> 7) * A16_MTILES + (m >> 4)) * 16 + ((k >> 3) & 15)) * 16 + (m & 15)) * 8 + (k & 7);
+constexpr int A16_MAX_ROWS = 128;                      // token rows per k block: steps of up to 128 tokens
+constexpr int A16_KB_HALVES = A16_MAX_ROWS * 128;      // halves per k block of a buffer
+__host__ __device__ inline size_t a16_index(int m, int k, int th) {
+    return (size_t)(k >> 7) * A16_KB_HALVES + ((size_t)((k >> 3) & 15) * th + m) * 8 + (k & 7);
 }
 
 __device__ __forceinline__ __half f2h_sat(float v) {

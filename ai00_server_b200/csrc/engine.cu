@@ -413,7 +413,7 @@ struct b200rwkv_engine {
     std::unique_ptr<Group> group;             // set on rank 0 of an in-process tensor-parallel engine
     b200rwkv_info info;
     int dev = 0, rank = 0, world = 1, num_sms = 148;
-    int S = 0, chunk = 0, maxT = 16 * A16_MTILES, precision = 0;      // steps of up to 128 tokens
+    int S = 0, chunk = 0, maxT = A16_MAX_ROWS, precision = 0;      // steps of up to 128 tokens
     int L = 0, C = 0, F = 0, V = 0, H = 0, N = 64, Cl = 0, Hl = 0, Fl = 0, Vl = 0;
     bool use_graph = true, use_pdl = true;
     int split_att = 1, split_ffn = 1;
@@ -463,7 +463,7 @@ struct b200rwkv_engine {
     std::map<int, long long> graph_launches;   // kernels per captured step graph
     long long launch_total = 0;                // kernels launched by this engine's steps since creation
     long long launches_last_step = 0;
-    int last_T = 0;
+    int last_T = 0, last_th = 16;      // tokens / A16 token rows of the most recent step
 
     // softmax
     float *sm_in = nullptr, *sm_out = nullptr;
@@ -1266,6 +1266,10 @@ void b200rwkv_engine::finalize_tp() {
 void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* prof) {
     launches_last_step = 0;
     const int rows = MT * 16;
+    // token rows of this step's A16 operands (common.cuh): every producer and consumer of the step uses the same value
+    const int th = (split_on && MT == 1) ? 32 : 16 * MT;
+    const int th_rows = (split_on && MT == 1) ? 32 : 16 * MTR;        // the head's operand holds output rows
+    last_th = th;
     auto pre_skipped = [&](const Layer& ly, int gi) {
         if (fold_wd2 && gi == ly.wd2_index) return true;                 // the WKV kernel evaluates the decay LoRA stage 2
         return fused_pre_ok && MT == 1 && ly.w1_raw && gi < 2;           // the front-half kernel holds both ddlerp LoRA stages
@@ -1300,6 +1304,8 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             g2.p.next_grid = nx.grid;
             g2.p.prefetch_blocks = prefetch_blocks;
         }
+        for (int i = 0; i < g2.p.nseg; ++i)
+            if (g2.p.seg[i].out_mode != OUT_F32) g2.p.seg[i].ldo = th;      // A16 outputs feed a projection of this step
         launch_gemm(g2, mt, s, prof, split_on && MT == 1);      // split operands only when the whole step is decode-shaped
     };
     auto gemm = [&](const GemmLaunch& g) { launch_gemm_chained(g, MT); };
@@ -1307,6 +1313,7 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
     auto launch_ln = [&](const LnMixParams& lp0) {
         LnMixParams lp = lp0;
         lp.trace = tr_next(0);
+        lp.kq_tile = th;
         if (ln_cluster_ok && MT == 1) {
             launch_cluster = PRE_CLUSTER;
             if (split_on) launch_k(ln_mix_cluster_kernel<true>, dim3(PRE_GRID), dim3(PRE_THREADS), 0, lp, KC_LN, s, prof);
@@ -1325,6 +1332,7 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             memset(&q, 0, sizeof(q));
             q.ln = ly.ln1;
             q.ln.trace = tr_next(6);
+            q.ln.kq_tile = th;
             q.W1 = ly.w1_raw; q.W2 = ly.w2_raw;
             for (int j = 0; j < 5; ++j) { q.mu[j] = ly.mu5[j]; q.out[j] = a_x[j].p; }
             q.lora = a_lora[0].p; q.lora_stride = (int)a_lora[0].halves_per_matrix; q.lora_kq = a_lora[0].kq;
@@ -1347,6 +1355,7 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             // decays / staged rows are sized by the step shape: a slot cannot hold more tokens than the step
             WkvParams wp = ly.wkv;
             wp.trace = tr_next(2);
+            wp.kq_tile = th; wp.d1_kq = th;
             const bool sp = split_on && MT == 1;
             const size_t sm_b = wkv_smem_bytes(info.version, fold_wd2, info.time_decay_adapter, rows, sp);
             switch (info.version * 2 + (sp ? 1 : 0)) {
@@ -1365,8 +1374,10 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
         if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
     }
     {
-        if (split_on && MT == 1) launch_k(ln_out_kernel<true>, dim3(rows), dim3(LN_THREADS), 0, lnout, KC_LN, s, prof);
-        else launch_k(ln_out_kernel<false>, dim3(rows), dim3(LN_THREADS), 0, lnout, KC_LN, s, prof);
+        LnOutParams lo = lnout;
+        lo.kq_tile = th_rows;
+        if (split_on && MT == 1) launch_k(ln_out_kernel<true>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
+        else launch_k(ln_out_kernel<false>, dim3(rows), dim3(LN_THREADS), 0, lo, KC_LN, s, prof);
     }
     if (MTR > 0) launch_gemm_chained(head, MTR);
     if (world > 1) launch_k(tp_barrier_kernel, dim3(1), dim3(32), 0, tpbar, KC_OTHER, s, prof);
@@ -2434,11 +2445,10 @@ int32_t b200rwkv_op_wkv(int32_t device, int32_t version, int32_t T, int32_t H, c
         p.a = up(a, TC, 0.f); p.nu = up(nullptr, TC, 0.f); p.v_first = up(nullptr, TC, 0.f); p.layer0 = 1;
         p.k_k = up(k_k, Cc, 0.f); p.k_a = up(k_a, Cc, 0.f); p.r_k = up(r_k, Cc, 0.f);
     }
-    const int kq = rup(Cc, GEMM_BK) / 32;
     const size_t halves = (size_t)(rup(Cc, GEMM_BK) / GEMM_BK) * A16_KB_HALVES;
     keep.push_back(new DevTmp(halves * 2));
     p.out = (__half*)keep.back()->p;
-    p.kq_tile = kq;
+    p.kq_tile = 64;                       // token rows of the A16 output: any value >= T the reader below agrees on
     CK(cudaMemset(p.out, 0, halves * 2));
     const size_t smem = wkv_smem_bytes(version, false, 0, maxT);
     switch (version) {
@@ -2451,7 +2461,7 @@ int32_t b200rwkv_op_wkv(int32_t device, int32_t version, int32_t T, int32_t H, c
     std::vector<__half> ho(halves);
     CK(cudaMemcpy(ho.data(), p.out, halves * 2, cudaMemcpyDeviceToHost));
     for (int t = 0; t < T; ++t)
-        for (int c = 0; c < Cc; ++c) out[(size_t)t * Cc + c] = __half2float(ho[a16_index(t, c, kq)]);
+        for (int c = 0; c < Cc; ++c) out[(size_t)t * Cc + c] = __half2float(ho[a16_index(t, c, 64)]);
     CK(cudaMemcpy(state, p.state, (size_t)H * 64 * 64 * 4, cudaMemcpyDeviceToHost));
     API_END
 }
@@ -2535,7 +2545,7 @@ int32_t b200rwkv_debug_read(b200rwkv_engine* e, const char* name, float* out, si
                 std::vector<__half> h(a.b->halves_per_matrix);
                 CK(cudaMemcpy(h.data(), a.b->p + (size_t)a.mat * a.b->halves_per_matrix, h.size() * 2, cudaMemcpyDeviceToHost));
                 for (int t = 0; t < T; ++t)
-                    for (int c = 0; c < a.cols; ++c) out[(size_t)t * a.cols + c] = __half2float(h[a16_index(t, c, a.b->kq)]);
+                    for (int c = 0; c < a.cols; ++c) out[(size_t)t * a.cols + c] = __half2float(h[a16_index(t, c, e->last_th)]);
                 return a.cols;
             }
         throw Error(B200RWKV_ERR_INVALID, "unknown debug buffer: " + n);

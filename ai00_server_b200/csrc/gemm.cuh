@@ -46,7 +46,7 @@ constexpr int GEMM_SMEM_BUDGET = 221184;     // 216 KB for stages
 // canonical K-major no-swizzle strides of the two operands in shared memory
 constexpr uint32_t GEMM_W_LBO = 16 * 128;    // weight stage [k8 chunk 16][row group 16][8 rows][16 B]
 constexpr uint32_t GEMM_W_SBO = 128;
-constexpr uint32_t GEMM_A_LBO = 2 * 128;     // token tile   [k8 chunk 16][row group 2][8 rows][16 B]
+constexpr uint32_t GEMM_A_LBO = 2 * 128;     // token operand [k8 chunk 16][16 MT rows][16 B]: MT x this (set in the MMA role)
 constexpr uint32_t GEMM_A_SBO = 128;
 
 enum OutMode : int {
@@ -161,8 +161,9 @@ template <int MT, int NSTAGE, int STAGE_BYTES>
 __device__ __forceinline__ void gemm_mma_role(const GemmParams& p, const int b0, const int b1, const uint32_t smem_base,
                                               const uint32_t full_bar, const uint32_t empty_bar, const uint32_t tfull_bar,
                                               const uint32_t tempty_bar, const uint32_t tmem_base, RingPos& rp, unsigned& segcount) {
-    constexpr uint32_t IDESC = umma_idesc_f16(GEMM_BN, 16);
-    const uint32_t w_lbo = p.w_lbo, w_sbo = p.w_sbo, a_lbo = p.a_lbo, a_sbo = p.a_sbo;
+    constexpr uint32_t IDESC = umma_idesc_f16(GEMM_BN, 16 * MT);
+    const uint32_t w_lbo = p.w_lbo, w_sbo = p.w_sbo, a_sbo = p.a_sbo;
+    constexpr uint32_t a_lbo = 16 * MT * 16;          // bytes between the k8 chunks of the token operand: 16 MT rows x 16 B
     SegWalk w;
     w.init(p, b0, b1);
     while (!w.done()) {
@@ -175,14 +176,13 @@ __device__ __forceinline__ void gemm_mma_role(const GemmParams& p, const int b0,
             mbar_wait(full_bar + rp.stage * 8, rp.phase, 12);
             tc_fence_after();
             const uint32_t st = smem_base + rp.stage * STAGE_BYTES;
+            // one MMA per k16 step over all 16 x MT token rows of the stage (N = 16 MT): the token operand of a stage is one
+            // canonical tile [k8 chunk][16 MT rows][16 B] (common.cuh), chunk stride = 16 MT x 16 bytes
 #pragma unroll
             for (int k16 = 0; k16 < GEMM_BK / 16; ++k16) {
                 const uint64_t adesc = umma_desc(st + k16 * 2 * w_lbo, w_lbo, w_sbo);
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const uint64_t bdesc = umma_desc(st + GEMM_WBYTES + mt * GEMM_ABYTES + k16 * 2 * a_lbo, a_lbo, a_sbo);
-                    tc_mma_f16(d0 + mt * 16, adesc, bdesc, IDESC, (i > 0 || k16 > 0) ? 1u : 0u);
-                }
+                const uint64_t bdesc = umma_desc(st + GEMM_WBYTES + k16 * 2 * a_lbo, a_lbo, a_sbo);
+                tc_mma_f16(d0, adesc, bdesc, IDESC, (i > 0 || k16 > 0) ? 1u : 0u);
             }
             tc_commit(empty_bar + rp.stage * 8);          // slot is free once these MMAs have read it
             rp.advance<NSTAGE>(1);

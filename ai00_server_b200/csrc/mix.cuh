@@ -40,7 +40,7 @@ struct LnMixParams {
     int n_mix;
     const float* mu[6];
     __half* mix_out[6];
-    int kq_tile;            // C / 32
+    int kq_tile;            // th: token rows of this step's A16 operands (16 x token tiles; 32 with split operands)
     float* xx_out;          // [T, C]
     float* sx_out;          // [T, C] or null
     float* commit_dst;      // [S, C] or null

@@ -44,7 +44,7 @@ struct Pre6Params {
     const float* mu[5];       // time_mix_{w,k,v,r,g}
     __half* lora;             // five A16 [16][Dm] matrices: tanh(W1 xxx)
     int lora_stride;          // halves between them
-    int lora_kq;              // k32 blocks per 16-token tile of those matrices (split operands: lo halves live in tile 1)
+    int lora_kq;              // (unused: the token-row count of the A16 operands is 16, or 32 with split operands)
     __half* out[5];           // A16 [16][C] operands of decay-LoRA, K, V, R, G
     int Dm;
     unsigned* gbar;           // two arrival counters, 128 bytes apart
@@ -214,13 +214,13 @@ __device__ __forceinline__ void pre_ln_slice(const LnMixParams& p, const int t, 
                 uint2 hi, lo;
                 split_pack_h2(a.x + sx.x * mu.x, a.y + sx.y * mu.y, hi.x, lo.x);
                 split_pack_h2(a.z + sx.z * mu.z, a.w + sx.w * mu.w, hi.y, lo.y);
-                *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t, c, p.kq_tile)) = hi;
-                *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t + 16, c, p.kq_tile)) = lo;
+                *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t, c, 32)) = hi;
+                *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t + 16, c, 32)) = lo;
             } else {
                 uint2 o;
                 o.x = pack_h2(a.x + sx.x * mu.x, a.y + sx.y * mu.y);
                 o.y = pack_h2(a.z + sx.z * mu.z, a.w + sx.w * mu.w);
-                *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t, c, p.kq_tile)) = o;
+                *reinterpret_cast<uint2*>(p.mix_out[m] + a16_index(t, c, 16)) = o;
             }
         }
     }
@@ -257,6 +257,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
     const int g = blockIdx.x / PRE_CLUSTER;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 2, tig = lane & 3;
     constexpr int Dm = KD * 16;
+    constexpr int TH = SPLIT ? 32 : 16;                         // token rows of the A16 operands of a decode-shaped step
     constexpr int NR = 5 * Dm;                                  // LoRA rows
     constexpr int RG = (NR + PRE_NCLUSTER - 1) / PRE_NCLUSTER;  // rows per cluster (10 / 20)
     static_assert(RG <= PRE_NT2 * 8, "row group does not fit the n-tiles");
@@ -338,12 +339,12 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
             for (int i = 0; i < PRE_KSW; ++i) {
                 const int kstep = warp + 8 * i;
                 const int k = (int)rank * Cs + kstep * 16;     // a 16-wide k step never straddles a 128-wide k block
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(xa + a16_index(16 * sp + grp, k + tig * 2));
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(xa + a16_index(16 * sp + grp, k + tig * 2, TH));
                 const bool ok = kstep < ksteps;
-                af[i][0] = ok ? __ldcg(src) : 0u;               // (t = grp,     k lo)
-                af[i][1] = ok ? __ldcg(src + 32) : 0u;          // (t = grp + 8, k lo)   +64 halves
-                af[i][2] = ok ? __ldcg(src + 64) : 0u;          // (t = grp,     k hi)   next 8-wide chunk
-                af[i][3] = ok ? __ldcg(src + 96) : 0u;          // (t = grp + 8, k hi)
+                af[i][0] = ok ? __ldcg(src) : 0u;                       // (t = grp,     k lo)
+                af[i][1] = ok ? __ldcg(src + 32) : 0u;                  // (t = grp + 8, k lo)   +8 rows = 64 halves
+                af[i][2] = ok ? __ldcg(src + TH * 4) : 0u;              // (t = grp,     k hi)   next k8 chunk = TH rows on
+                af[i][3] = ok ? __ldcg(src + TH * 4 + 32) : 0u;         // (t = grp + 8, k hi)
             }
 #pragma unroll
             for (int i = 0; i < PRE_KSW; ++i)
@@ -381,10 +382,10 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
                 if (SPLIT) {
                     __half hi, lo;
                     split_h(apply_act(s, ACT_TANH), hi, lo);
-                    dst[a16_index(t, nn, p.lora_kq)] = hi;
-                    dst[a16_index(t + 16, nn, p.lora_kq)] = lo;
+                    dst[a16_index(t, nn, TH)] = hi;
+                    dst[a16_index(t + 16, nn, TH)] = lo;
                 } else {
-                    dst[a16_index(t, nn)] = f2h_sat(apply_act(s, ACT_TANH));
+                    dst[a16_index(t, nn, TH)] = f2h_sat(apply_act(s, ACT_TANH));
                 }
             }
         }
@@ -407,13 +408,13 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
             for (int i = 0; i < PRE_TILES3; ++i) {
                 const bool ok = tj[i] >= 0;
                 const uint32_t* src = reinterpret_cast<const uint32_t*>(p.lora + (size_t)(ok ? tj[i] : 0) * p.lora_stride +
-                                                                        a16_index(16, 0, p.lora_kq) + (size_t)grp * 8 + tig * 2);
+                                                                        a16_index(16 + grp, tig * 2, TH));
 #pragma unroll
-                for (int ks = 0; ks < KD; ++ks) {
-                    af[i][ks][0] = ok ? __ldcg(src + ks * 128) : 0u;
-                    af[i][ks][1] = ok ? __ldcg(src + ks * 128 + 32) : 0u;
-                    af[i][ks][2] = ok ? __ldcg(src + ks * 128 + 64) : 0u;
-                    af[i][ks][3] = ok ? __ldcg(src + ks * 128 + 96) : 0u;
+                for (int ks = 0; ks < KD; ++ks) {      // k16 step ks = k8 chunks 2 ks, 2 ks + 1 (TH rows x 8 halves each)
+                    af[i][ks][0] = ok ? __ldcg(src + ks * TH * 8) : 0u;
+                    af[i][ks][1] = ok ? __ldcg(src + ks * TH * 8 + 32) : 0u;
+                    af[i][ks][2] = ok ? __ldcg(src + ks * TH * 8 + TH * 4) : 0u;
+                    af[i][ks][3] = ok ? __ldcg(src + ks * TH * 8 + TH * 4 + 32) : 0u;
                 }
             }
 #pragma unroll
@@ -424,13 +425,13 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < PRE_TILES3; ++i) {
             const bool ok = tj[i] >= 0;
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.lora + (size_t)(ok ? tj[i] : 0) * p.lora_stride + (size_t)grp * 8 + tig * 2);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.lora + (size_t)(ok ? tj[i] : 0) * p.lora_stride + a16_index(grp, tig * 2, TH));
 #pragma unroll
             for (int ks = 0; ks < KD; ++ks) {
-                af[i][ks][0] = ok ? __ldcg(src + ks * 128) : 0u;             // chunk 2*ks, t = grp
-                af[i][ks][1] = ok ? __ldcg(src + ks * 128 + 32) : 0u;        //             t = grp + 8
-                af[i][ks][2] = ok ? __ldcg(src + ks * 128 + 64) : 0u;        // chunk 2*ks + 1
-                af[i][ks][3] = ok ? __ldcg(src + ks * 128 + 96) : 0u;
+                af[i][ks][0] = ok ? __ldcg(src + ks * TH * 8) : 0u;                  // chunk 2*ks, t = grp
+                af[i][ks][1] = ok ? __ldcg(src + ks * TH * 8 + 32) : 0u;             //             t = grp + 8
+                af[i][ks][2] = ok ? __ldcg(src + ks * TH * 8 + TH * 4) : 0u;         // chunk 2*ks + 1
+                af[i][ks][3] = ok ? __ldcg(src + ks * TH * 8 + TH * 4 + 32) : 0u;
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -461,10 +462,10 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
                 if (SPLIT) {
                     uint32_t hi, lo;
                     split_pack_h2(y0, y1, hi, lo);
-                    *reinterpret_cast<uint32_t*>(outp + a16_index(t, tc0[i] + tig * 2, p.ln.kq_tile)) = hi;
-                    *reinterpret_cast<uint32_t*>(outp + a16_index(t + 16, tc0[i] + tig * 2, p.ln.kq_tile)) = lo;
+                    *reinterpret_cast<uint32_t*>(outp + a16_index(t, tc0[i] + tig * 2, TH)) = hi;
+                    *reinterpret_cast<uint32_t*>(outp + a16_index(t + 16, tc0[i] + tig * 2, TH)) = lo;
                 } else {
-                    *reinterpret_cast<uint32_t*>(outp + a16_index(t, tc0[i] + tig * 2, p.ln.kq_tile)) = pack_h2(y0, y1);
+                    *reinterpret_cast<uint32_t*>(outp + a16_index(t, tc0[i] + tig * 2, TH)) = pack_h2(y0, y1);
                 }
             }
         }
