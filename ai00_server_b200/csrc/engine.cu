@@ -1814,7 +1814,6 @@ static int32_t create_rank(const uint8_t* st, size_t len, int32_t device, int32_
     REQUIRE(out, B200RWKV_ERR_INVALID, "null out");
     *out = nullptr;
     REQUIRE(precision == 0 || precision == 1, B200RWKV_ERR_INVALID, "precision must be 0 (fp16) or 1 (fp32)");
-    REQUIRE(precision == 0 || world == 1, B200RWKV_ERR_UNSUPPORTED, "precision 1 (f32 activations) is single-GPU only");
     REQUIRE(max_batch >= 1 && max_batch <= 1024, B200RWKV_ERR_INVALID, "max_batch out of range");
     REQUIRE(token_chunk_size >= 1, B200RWKV_ERR_INVALID, "token_chunk_size must be >= 1");
     REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, B200RWKV_ERR_INVALID, "bad rank/world");

@@ -304,22 +304,21 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
             }
             constexpr int MTE = SPLIT ? 1 : MT;        // token tiles the epilogue writes
             if (n < segN) {
+                // Everything below is unrolled over the token tiles with compile-time register indices: a dynamically
+                // indexed copy of the accumulator lands in local memory, and next to a 200 KB ring the L1 is too small to hold
+                // it -- measured (r02_findings.md §8): 128-token steps spent 0.6 us of L2 latency per token and row there.
                 const float bias = biasp ? biasp[n] : 0.f;
-                float lv[MT * 16];                     // dynamically indexed below -> local memory, rolled loop
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) lv[mt * 16 + j] = v[mt][j];
                 const int mmax = min(nrows, MTE * 16);
                 if (out_mode == OUT_F32) {
                     float* o = reinterpret_cast<float*>(outp) + n;
-                    if (MTE == 1) {         // decode shape: straight from registers, all 16 stores in flight
 #pragma unroll
-                        for (int m = 0; m < 16; ++m)
-                            if (m < mmax) o[(size_t)m * ldo] = apply_act(v[0][m] + bias, act);
-                    } else {
-#pragma unroll 1
-                        for (int m = 0; m < mmax; ++m) o[(size_t)m * ldo] = apply_act(lv[m] + bias, act);
+                    for (int mt = 0; mt < MTE; ++mt) {
+                        if (mt * 16 >= mmax) break;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int m = mt * 16 + j;
+                            if (m < mmax) o[(size_t)m * ldo] = apply_act(v[mt][j] + bias, act);
+                        }
                     }
                 } else {
                     __half* base = reinterpret_cast<__half*>(outp);
@@ -329,24 +328,27 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
                         base += (size_t)gi * grp_stride;
                         nn = n - gi * grp;
                     }
-                    const float mu = (out_mode == OUT_LERP_A16) ? aux2[n] : 0.f;
-#pragma unroll 1
-                    for (int m0 = 0; m0 < mmax; m0 += 4) {
-                        // the two lerp operands of four tokens are requested together (L2 latency bound)
-                        float x0[4], x1[4];
+                    const bool lerp = (out_mode == OUT_LERP_A16);
+                    const float mu = lerp ? aux2[n] : 0.f;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const bool ok = (out_mode == OUT_LERP_A16) && (m0 + u < mmax);
-                            const size_t a_ = (size_t)(m0 + u) * ld_aux + n;
-                            x0[u] = ok ? aux0[a_] : 0.f;
-                            x1[u] = ok ? aux1[a_] : 0.f;
+                    for (int mt = 0; mt < MTE; ++mt) {
+                        if (mt * 16 >= mmax) break;
+                        // the lerp operands of the tile's 16 tokens are requested together (L2 latency bound)
+                        float x0[16], x1[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int m = mt * 16 + j;
+                            const bool ok = lerp && m < mmax;
+                            const size_t a_ = (size_t)m * ld_aux + n;
+                            x0[j] = ok ? aux0[a_] : 0.f;
+                            x1[j] = ok ? aux1[a_] : 0.f;
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int m = m0 + u;
+                        for (int j = 0; j < 16; ++j) {
+                            const int m = mt * 16 + j;
                             if (m < mmax) {
-                                float y = apply_act(lv[m] + bias, act);
-                                if (out_mode == OUT_LERP_A16) y = x0[u] + x1[u] * (mu + y);
+                                float y = apply_act(v[mt][j] + bias, act);
+                                if (lerp) y = x0[j] + x1[j] * (mu + y);
                                 if (SPLIT) {
                                     __half hi, lo;
                                     split_h(y, hi, lo);

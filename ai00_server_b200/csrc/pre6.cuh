@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(PRE_THREADS) ln_mix_cluster_kernel(const __gri
     trace_stamp(p.trace, 0);
     pdl_launch_dependents();
     const PreLnStatic<6> st = pre_ln_static<6>(p, t, rank);
+    cl.sync();       // every CTA of the cluster is executing before anyone writes into a peer's shared memory (off the critical path)
     pdl_wait();
     trace_stamp(p.trace, 1);
     if (t >= st.T) return;                // uniform over the cluster
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(PRE_THREADS, 2) pre6_kernel(const __grid_const
         }
         mu3[i] = ok ? *reinterpret_cast<const float2*>(p.mu[j] + tc0[i] + tig * 2) : make_float2(0.f, 0.f);
     }
+    cl.sync();       // every CTA of the cluster is executing before anyone writes into a peer's shared memory (off the critical path)
     pdl_wait();
     trace_stamp(tr, 1);
     cta_stamp(1);

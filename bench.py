@@ -478,6 +478,19 @@ def main():
                 "step_frac": alg_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "step_ms_p10_p50_p90": [float(np.percentile(step_ms_dist, q)) for q in (10, 50, 90)] if step_ms_dist.size else None}
 
+    # ---- the parity path beside the throughput path: precision 1 (f32-exact activations) on the same workload ----
+    exact_rec = None
+    if world == 1 and not args.exact and os.environ.get("B200RWKV_BENCH_SKIP_EXACT") != "1":
+        m2 = runtime.Model(st, max_batch=BATCH, token_chunk_size=64, device=dev, exact=True)
+        for s_ in slots:
+            m2.state.load(zero, s_)
+        m2.infer_raw(slots, [PROMPT] * BATCH, toks[:, :PROMPT].reshape(-1).tolist(), [2] * BATCH)
+        ms2, _ = m2.bench_decode(slots, dec, args.warmup, args.steps)
+        exact_rec = {"ms_per_step": ms2 / args.steps, "value": BATCH * args.steps / (ms2 * 1e-3), "unit": "tokens/s",
+                     "what": "b200rwkv_create(precision = 1): split f16 hi+lo operands, no activation rounded; logits within 1.6e-4 of the "
+                             "f32 oracle at the 7B shape (tests/test_gpu_zfullsize.py, profiles/r02_parity_fullsize.jsonl)"}
+        m2.close()
+
     # ---- cpu baseline (rank 0, N=1 only) ----
     cpu = None
     if world == 1 and args.cpu_steps > 0:
@@ -492,7 +505,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "build_seconds": build_s}
+            "precision1": exact_rec, "build_seconds": build_s}
     print(json.dumps(line))
     barrier()
     model.close()

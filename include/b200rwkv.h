@@ -71,7 +71,7 @@ int32_t b200rwkv_info_from_st(const uint8_t* st, size_t len, b200rwkv_info* out)
  * are f16 on disk and in HBM either way):
  *   0 = fp16: every projection input is rounded to f16 (tensor-core operand), f32 accumulate / state / logits;
  *   1 = fp32: no activation is rounded -- every projection input travels as an f16 hi + lo pair (two operand tiles,
- *       accumulators added), which is f32-exact to ~2^-22; steps are capped at 16 tokens; single GPU. */
+ *       accumulators added), which is f32-exact to ~2^-22; steps are capped at 16 tokens. */
 int32_t b200rwkv_create(const uint8_t* st, size_t len, int32_t device, int32_t max_batch,
                         int32_t token_chunk_size, int32_t precision, b200rwkv_engine** out);
 

@@ -35,6 +35,17 @@ def test_tp_matches_single_gpu():
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs at least 2 GPUs")
+def test_tp_matches_single_gpu_with_f32_activations():
+    """precision 1 (split hi + lo operands) under tensor parallelism: the sharded engine and the single-GPU engine differ only
+    in f32 summation order -> 1e-4."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={_world()}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "tp_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, B200RWKV_TEST_EXACT="1"))
+    assert out.returncode == 0 and "TP_OK" in out.stdout, (out.stdout[-2000:], out.stderr[-3000:])
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs at least 2 GPUs")
 def test_one_engine_object_drives_all_ranks():
     """b200rwkv_create_ex with several devices: ONE handle owns every tensor-parallel rank (the reference's single Runtime
     object, run.rs:1230-1234): same logits as the single-GPU engine, states merged by head in State::back and scattered in

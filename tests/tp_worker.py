@@ -20,9 +20,10 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    exact = os.environ.get("B200RWKV_TEST_EXACT") == "1"          # precision 1 (f32 activations) on both sides
     for preset in sys.argv[1:] or ["small6", "small7", "small5"]:          # 8 heads each: every world size up to 8 divides them
         st = synth.make_st(preset, 0)
-        m = runtime.Model(st, max_batch=4, token_chunk_size=32, device=local, rank=rank, world=world)
+        m = runtime.Model(st, max_batch=4, token_chunk_size=32, device=local, rank=rank, world=world, exact=exact)
         tp.connect(m)
         rng = np.random.default_rng(3)
         runs = [rng.integers(1, 500, size=n).tolist() for n in (5, 1, 7)]
@@ -34,15 +35,16 @@ def main():
         for _ in range(3):                                     # decode steps on top
             got2 = np.concatenate(m.infer_raw([0, 1, 2], [1, 1, 1], [9, 8, 7], [capi.OPTION_LAST] * 3))
         if rank == 0:
-            single = runtime.Model(st, max_batch=4, token_chunk_size=32, device=local)
+            single = runtime.Model(st, max_batch=4, token_chunk_size=32, device=local, exact=exact)
             for s in range(3):
                 single.state.load(single.state.init(), s)
             want = np.concatenate(single.infer_raw(*args))
             for _ in range(3):
                 want2 = np.concatenate(single.infer_raw([0, 1, 2], [1, 1, 1], [9, 8, 7], [capi.OPTION_LAST] * 3))
             e1, e2 = rel_err(got, want), rel_err(got2, want2)
-            ok = e1 <= 1e-3 and e2 <= 1e-3 and (got.argmax(1) == want.argmax(1)).all() and (got2.argmax(1) == want2.argmax(1)).all()
-            print(f"{preset}: world={world} prefill rel={e1:.2e} decode rel={e2:.2e} argmax_ok={ok}", flush=True)
+            tol = 1e-4 if exact else 1e-3          # f32 activations: only the f32 summation order differs between the shardings
+            ok = e1 <= tol and e2 <= tol and (got.argmax(1) == want.argmax(1)).all() and (got2.argmax(1) == want2.argmax(1)).all()
+            print(f"{preset}: world={world} exact={exact} prefill rel={e1:.2e} decode rel={e2:.2e} argmax_ok={ok}", flush=True)
             assert ok
             single.close()
         dist.barrier()
