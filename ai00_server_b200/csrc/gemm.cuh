@@ -29,6 +29,8 @@
 //   * a launch carries up to 8 "segments" (independent matrices, own input, K and epilogue) so
 //     R/K/V/G + decay-LoRA, or the five ddlerp LoRAs, go out as ONE kernel.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -304,58 +306,110 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
             }
             constexpr int MTE = SPLIT ? 1 : MT;        // token tiles the epilogue writes
             if (n < segN) {
-                // Everything below is unrolled over the token tiles with compile-time register indices: a dynamically
-                // indexed copy of the accumulator lands in local memory, and next to a 200 KB ring the L1 is too small to hold
-                // it -- measured (r02_findings.md §8): 128-token steps spent 0.6 us of L2 latency per token and row there.
                 const float bias = biasp ? biasp[n] : 0.f;
                 const int mmax = min(nrows, MTE * 16);
-                if (out_mode == OUT_F32) {
-                    float* o = reinterpret_cast<float*>(outp) + n;
+                if (MTE > 1) {
+                    // Multi-tile steps (prefill): unrolled over tiles and tokens with compile-time register indices -- a
+                    // dynamically indexed copy of the accumulator lands in local memory, and next to a 200 KB ring the L1 cannot
+                    // hold it (r02_findings.md §8).  The activation is a template parameter of the unrolled body, otherwise the
+                    // run-time switch is replicated 16 MT times and the epilogue no longer fits the instruction cache.
+                    auto body = [&](auto act_c) {
+                        constexpr int ACT_C = decltype(act_c)::value;
+                        if (out_mode == OUT_F32) {
+                            float* o = reinterpret_cast<float*>(outp) + n;
 #pragma unroll
-                    for (int mt = 0; mt < MTE; ++mt) {
-                        if (mt * 16 >= mmax) break;
+                            for (int mt = 0; mt < MTE; ++mt)
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int m = mt * 16 + j;
-                            if (m < mmax) o[(size_t)m * ldo] = apply_act(v[mt][j] + bias, act);
+                                for (int j = 0; j < 16; ++j) {
+                                    const int m = mt * 16 + j;
+                                    if (m < mmax) o[(size_t)m * ldo] = apply_act(v[mt][j] + bias, ACT_C);
+                                }
+                        } else {
+                            __half* base = reinterpret_cast<__half*>(outp);
+                            int nn = n;
+                            if (grp > 0) {
+                                const int gi = n / grp;
+                                base += (size_t)gi * grp_stride;
+                                nn = n - gi * grp;
+                            }
+                            const bool lerp = (out_mode == OUT_LERP_A16);
+                            const float mu = lerp ? aux2[n] : 0.f;
+#pragma unroll
+                            for (int mt = 0; mt < MTE; ++mt) {
+                                float x0[16], x1[16];          // the lerp operands of a tile's 16 tokens are requested together
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const int m = mt * 16 + j;
+                                    const bool ok = lerp && m < mmax;
+                                    const size_t a_ = (size_t)m * ld_aux + n;
+                                    x0[j] = ok ? aux0[a_] : 0.f;
+                                    x1[j] = ok ? aux1[a_] : 0.f;
+                                }
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const int m = mt * 16 + j;
+                                    if (m < mmax) {
+                                        float y = apply_act(v[mt][j] + bias, ACT_C);
+                                        if (lerp) y = x0[j] + x1[j] * (mu + y);
+                                        base[a16_index(m, nn, ldo)] = f2h_sat(y);
+                                    }
+                                }
+                            }
                         }
+                    };
+                    switch (act) {
+                        case ACT_TANH: body(std::integral_constant<int, ACT_TANH>{}); break;
+                        case ACT_SIGMOID: body(std::integral_constant<int, ACT_SIGMOID>{}); break;
+                        case ACT_SILU: body(std::integral_constant<int, ACT_SILU>{}); break;
+                        case ACT_RELU2: body(std::integral_constant<int, ACT_RELU2>{}); break;
+                        case ACT_EXPNEGEXP: body(std::integral_constant<int, ACT_EXPNEGEXP>{}); break;
+                        case ACT_V7DECAY: body(std::integral_constant<int, ACT_V7DECAY>{}); break;
+                        default: body(std::integral_constant<int, ACT_NONE>{}); break;
                     }
                 } else {
-                    __half* base = reinterpret_cast<__half*>(outp);
-                    int nn = n;
-                    if (grp > 0) {
-                        const int gi = n / grp;
-                        base += (size_t)gi * grp_stride;
-                        nn = n - gi * grp;
-                    }
-                    const bool lerp = (out_mode == OUT_LERP_A16);
-                    const float mu = lerp ? aux2[n] : 0.f;
+                    // one token tile (decode, and split operands after the hi + lo accumulators were added)
+                    if (out_mode == OUT_F32) {
+                        float* o = reinterpret_cast<float*>(outp) + n;
 #pragma unroll
-                    for (int mt = 0; mt < MTE; ++mt) {
-                        if (mt * 16 >= mmax) break;
-                        // the lerp operands of the tile's 16 tokens are requested together (L2 latency bound)
-                        float x0[16], x1[16];
+                        for (int m = 0; m < 16; ++m)             // straight from registers, all 16 stores in flight
+                            if (m < mmax) o[(size_t)m * ldo] = apply_act(v[0][m] + bias, act);
+                    } else {
+                        float lv[16];                            // dynamically indexed below: 64 bytes of local memory
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int m = mt * 16 + j;
-                            const bool ok = lerp && m < mmax;
-                            const size_t a_ = (size_t)m * ld_aux + n;
-                            x0[j] = ok ? aux0[a_] : 0.f;
-                            x1[j] = ok ? aux1[a_] : 0.f;
+                        for (int j = 0; j < 16; ++j) lv[j] = v[0][j];
+                        __half* base = reinterpret_cast<__half*>(outp);
+                        int nn = n;
+                        if (grp > 0) {
+                            const int gi = n / grp;
+                            base += (size_t)gi * grp_stride;
+                            nn = n - gi * grp;
                         }
+                        const float mu = (out_mode == OUT_LERP_A16) ? aux2[n] : 0.f;
+#pragma unroll 1
+                        for (int m0 = 0; m0 < mmax; m0 += 4) {
+                            // the two lerp operands of four tokens are requested together (L2 latency bound)
+                            float x0[4], x1[4];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int m = mt * 16 + j;
-                            if (m < mmax) {
-                                float y = apply_act(v[mt][j] + bias, act);
-                                if (lerp) y = x0[j] + x1[j] * (mu + y);
-                                if (SPLIT) {
-                                    __half hi, lo;
-                                    split_h(y, hi, lo);
-                                    base[a16_index(m, nn, ldo)] = hi;
-                                    base[a16_index(m + 16, nn, ldo)] = lo;
-                                } else {
-                                    base[a16_index(m, nn, ldo)] = f2h_sat(y);
+                            for (int u = 0; u < 4; ++u) {
+                                const bool ok = (out_mode == OUT_LERP_A16) && (m0 + u < mmax);
+                                const size_t a_ = (size_t)(m0 + u) * ld_aux + n;
+                                x0[u] = ok ? aux0[a_] : 0.f;
+                                x1[u] = ok ? aux1[a_] : 0.f;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int m = m0 + u;
+                                if (m < mmax) {
+                                    float y = apply_act(lv[m] + bias, act);
+                                    if (out_mode == OUT_LERP_A16) y = x0[u] + x1[u] * (mu + y);
+                                    if (SPLIT) {
+                                        __half hi, lo;
+                                        split_h(y, hi, lo);
+                                        base[a16_index(m, nn, ldo)] = hi;
+                                        base[a16_index(m + 16, nn, ldo)] = lo;
+                                    } else {
+                                        base[a16_index(m, nn, ldo)] = f2h_sat(y);
+                                    }
                                 }
                             }
                         }
