@@ -8,7 +8,7 @@ from ai00_server_b200 import capi, runtime, synth
 preset = os.environ.get("B200RWKV_BENCH_PRESET", "v6-7b")
 B = int(os.environ.get("B200RWKV_BENCH_BATCH", "16"))
 st = synth.make_st(preset, 0)
-m = runtime.Model(st, max_batch=B, token_chunk_size=64)
+m = runtime.Model(st, max_batch=B, token_chunk_size=128)
 slots = list(range(B))
 rng = np.random.default_rng(0)
 for i in range(8):
