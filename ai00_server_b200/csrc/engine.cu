@@ -345,6 +345,7 @@ enum KClass { KC_GEMM = 0, KC_WKV = 1, KC_LN = 2, KC_OTHER = 3 };
 struct GemmLaunch {
     GemmParams p;
     int grid = 0;
+    int grid_wide = 0;         // grid of steps with >= 64 tokens: whole tiles per CTA (see make_launch)
     int total_tiles = 0;
     size_t weight_bytes = 0;   // algorithmic (unpadded) f16 weight bytes streamed
 };
@@ -720,6 +721,16 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
             for (int cand = num_sms; cand * 4 >= num_sms * 3; --cand)
                 if (tile % cand == 0) { g.grid = cand; break; }
     }
+    // Steps of 64 / 128 tokens: a partial accumulator tile is 32 / 64 KB per contributor, and the last arriver of a cut tile
+    // spends tens of microseconds summing them (measured: 3B K+R at 128 tokens, last MMA at 9-15 us, slowest CTA exits at
+    // 82 us; profiles/r02_steptrace_prefill128_3b.log).  Those steps run whole tiles per CTA, even if that leaves SMs idle.
+    g.grid_wide = g.grid;
+    if (force_grid <= 0) {
+        if (tile <= num_sms) g.grid_wide = tile;
+        else
+            for (int cand = num_sms; cand * 2 >= num_sms; --cand)        // several whole tiles per CTA; else keep stream-K
+                if (tile % cand == 0) { g.grid_wide = cand; break; }
+    }
     const int per_cta = std::max(1, blk / g.grid);
     g.p.max_contrib = cdiv(kbmax, per_cta) + 1;
     g.p.counters = (unsigned*)dalloc((size_t)tile * 4, true);
@@ -778,8 +789,8 @@ void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, P
             else launch_k(gemm_kernel<1, 2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<1, 2>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
             break;
         case 2: launch_k(gemm_kernel<2>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<2>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
-        case 4: launch_k(gemm_kernel<4>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<4>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
-        default: launch_k(gemm_kernel<8>, dim3(g.grid), dim3(GEMM_THREADS), GemmCfg<8>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
+        case 4: launch_k(gemm_kernel<4>, dim3(g.grid_wide), dim3(GEMM_THREADS), GemmCfg<4>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
+        default: launch_k(gemm_kernel<8>, dim3(g.grid_wide), dim3(GEMM_THREADS), GemmCfg<8>::SMEM_BYTES, g.p, KC_GEMM, s, prof); break;
     }
 }
 
@@ -1301,7 +1312,7 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             ++seq_pos;
             g2.p.next_W = nx.p.W;
             g2.p.next_blocks = nx.p.total_blocks;
-            g2.p.next_grid = nx.grid;
+            g2.p.next_grid = mt >= 4 ? nx.grid_wide : nx.grid;
             g2.p.prefetch_blocks = prefetch_blocks;
         }
         for (int i = 0; i < g2.p.nseg; ++i)
