@@ -671,6 +671,9 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
         SegDesc& d = segs[i];
         GemmSeg& sg = g.p.seg[i];
         sg = d.proto;
+        // A16 outputs are written as whole 16-byte chunks of 8 rows (gemm.cuh epilogue)
+        REQUIRE(sg.out_mode == OUT_F32 || (d.N % 8 == 0 && sg.grp % 8 == 0), B200RWKV_ERR_UNSUPPORTED,
+                "LoRA ranks / hidden size must be multiples of 8");
         sg.KB = cdiv(d.K, GEMM_BK);
         sg.tiles = cdiv(d.N, GEMM_BN);
         sg.N = d.N;

@@ -44,6 +44,7 @@ constexpr int GEMM_EPI_WARPS = 4;            // one per TMEM lane quarter
 constexpr int GEMM_EPI_THREADS = GEMM_EPI_WARPS * 32;
 constexpr int GEMM_THREADS = (GEMM_EPI_WARPS + 2) * 32;   // + MMA warp + TMA producer warp
 constexpr int GEMM_MAX_SEG = 8;
+constexpr int GEMM_STAGE_PITCH = 24;         // halves per row of the A16 epilogue staging buffer (16 tokens + padding, 48 B)
 constexpr int GEMM_SMEM_BUDGET = 221184;     // 216 KB for stages
 // canonical K-major no-swizzle strides of the two operands in shared memory
 constexpr uint32_t GEMM_W_LBO = 16 * 128;    // weight stage [k8 chunk 16][row group 16][8 rows][16 B]
@@ -204,7 +205,7 @@ __device__ __forceinline__ void gemm_mma_role(const GemmParams& p, const int b0,
 template <int MT, bool SPLIT = false>
 __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const int cta, const int G, const int b0, const int b1,
                                                    const uint32_t tfull_bar, const uint32_t tempty_bar, const uint32_t tmem_base,
-                                                   unsigned& segcount, const int nrows, volatile int* s_last_p,
+                                                   unsigned& segcount, const int nrows, volatile int* s_last_p, __half* s_stage,
                                                    unsigned long long* tr = nullptr) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned TB = (unsigned)p.total_blocks;
@@ -305,18 +306,23 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
                 for (int j = 0; j < 16; ++j) v[0][j] += v[MT - 1][j];
             }
             constexpr int MTE = SPLIT ? 1 : MT;        // token tiles the epilogue writes
-            if (n < segN) {
-                const float bias = biasp ? biasp[n] : 0.f;
-                const int mmax = min(nrows, MTE * 16);
-                if (MTE > 1) {
-                    // Multi-tile steps (prefill): unrolled over tiles and tokens with compile-time register indices -- a
-                    // dynamically indexed copy of the accumulator lands in local memory, and next to a 200 KB ring the L1 cannot
-                    // hold it (r02_findings.md §8).  The activation is a template parameter of the unrolled body, otherwise the
-                    // run-time switch is replicated 16 MT times and the epilogue no longer fits the instruction cache.
-                    auto body = [&](auto act_c) {
-                        constexpr int ACT_C = decltype(act_c)::value;
-                        if (out_mode == OUT_F32) {
-                            float* o = reinterpret_cast<float*>(outp) + n;
+            const bool row_ok = n < segN;
+            const float bias = (row_ok && biasp) ? biasp[n] : 0.f;
+            const int mmax = min(nrows, MTE * 16);
+            if (out_mode == OUT_F32) {
+                if (row_ok) {
+                    float* o = reinterpret_cast<float*>(outp) + n;
+                    if (MTE == 1) {         // decode shape: straight from registers, all 16 stores in flight
+#pragma unroll
+                        for (int m = 0; m < 16; ++m)
+                            if (m < mmax) o[(size_t)m * ldo] = apply_act(v[0][m] + bias, act);
+                    } else {
+                        // Multi-tile steps: unrolled over tiles and tokens with compile-time register indices (a dynamically
+                        // indexed copy of the accumulator would live in local memory, and next to a 200 KB ring there is no
+                        // L1 to hold it); the activation is a compile-time parameter of the unrolled body, otherwise the
+                        // run-time switch is replicated 16 MT times and the epilogue outgrows the instruction cache.
+                        auto body = [&](auto act_c) {
+                            constexpr int ACT_C = decltype(act_c)::value;
 #pragma unroll
                             for (int mt = 0; mt < MTE; ++mt)
 #pragma unroll
@@ -324,96 +330,102 @@ __device__ __forceinline__ void gemm_epilogue_role(const GemmParams& p, const in
                                     const int m = mt * 16 + j;
                                     if (m < mmax) o[(size_t)m * ldo] = apply_act(v[mt][j] + bias, ACT_C);
                                 }
-                        } else {
-                            __half* base = reinterpret_cast<__half*>(outp);
-                            int nn = n;
+                        };
+                        switch (act) {
+                            case ACT_TANH: body(std::integral_constant<int, ACT_TANH>{}); break;
+                            case ACT_SIGMOID: body(std::integral_constant<int, ACT_SIGMOID>{}); break;
+                            case ACT_SILU: body(std::integral_constant<int, ACT_SILU>{}); break;
+                            case ACT_RELU2: body(std::integral_constant<int, ACT_RELU2>{}); break;
+                            case ACT_EXPNEGEXP: body(std::integral_constant<int, ACT_EXPNEGEXP>{}); break;
+                            case ACT_V7DECAY: body(std::integral_constant<int, ACT_V7DECAY>{}); break;
+                            default: body(std::integral_constant<int, ACT_NONE>{}); break;
+                        }
+                    }
+                }
+            } else {
+                // A16 outputs (operand of a following projection).  Thread t holds output row n = one k index of that operand
+                // for 16 tokens; the layout wants, per token, 8 consecutive k in one 16-byte chunk.  Written straight from the
+                // registers that is one 2-byte store per token and row, four 32-byte sectors per warp instruction -- measured
+                // 33 us per 128-token tile (r02_findings.md §8).  So the tile is transposed through 6 KB of shared memory:
+                // every thread stages its 16 tokens, then writes two (token, chunk) pairs as 16-byte stores, 16 lanes = 256
+                // contiguous bytes.  All 128 epilogue threads take part (rows past the segment stage zeros).
+                const bool lerp = (out_mode == OUT_LERP_A16);
+                const float mu = (lerp && row_ok) ? aux2[n] : 0.f;
+                __half* const base0 = reinterpret_cast<__half*>(outp);
+                const int row0 = w.tile_local * GEMM_BN;         // first output row of this tile within the segment
+                auto stage_and_store = [&](const int mt, const __half (&h)[16], const int rowoff) {
+                    uint4 p0, p1;
+                    p0.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16);
+                    p0.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+                    p0.z = (uint32_t)__half_as_ushort(h[4]) | ((uint32_t)__half_as_ushort(h[5]) << 16);
+                    p0.w = (uint32_t)__half_as_ushort(h[6]) | ((uint32_t)__half_as_ushort(h[7]) << 16);
+                    p1.x = (uint32_t)__half_as_ushort(h[8]) | ((uint32_t)__half_as_ushort(h[9]) << 16);
+                    p1.y = (uint32_t)__half_as_ushort(h[10]) | ((uint32_t)__half_as_ushort(h[11]) << 16);
+                    p1.z = (uint32_t)__half_as_ushort(h[12]) | ((uint32_t)__half_as_ushort(h[13]) << 16);
+                    p1.w = (uint32_t)__half_as_ushort(h[14]) | ((uint32_t)__half_as_ushort(h[15]) << 16);
+                    *reinterpret_cast<uint4*>(s_stage + tid * GEMM_STAGE_PITCH) = p0;
+                    *reinterpret_cast<uint4*>(s_stage + tid * GEMM_STAGE_PITCH + 8) = p1;
+                    named_bar_sync(3, GEMM_EPI_THREADS);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int q = tid + GEMM_EPI_THREADS * i;
+                        const int c = q >> 4, m = q & 15;               // chunk of 8 rows, token of the tile
+                        const int nc = row0 + c * 8;                    // first output row of the chunk (N % 8 == 0: whole chunks)
+                        if (nc < segN && mt * 16 + m < mmax) {
+                            const __half* src = s_stage + (c * 8) * GEMM_STAGE_PITCH + m;
+                            uint4 o;
+                            o.x = (uint32_t)__half_as_ushort(src[0]) | ((uint32_t)__half_as_ushort(src[GEMM_STAGE_PITCH]) << 16);
+                            o.y = (uint32_t)__half_as_ushort(src[2 * GEMM_STAGE_PITCH]) | ((uint32_t)__half_as_ushort(src[3 * GEMM_STAGE_PITCH]) << 16);
+                            o.z = (uint32_t)__half_as_ushort(src[4 * GEMM_STAGE_PITCH]) | ((uint32_t)__half_as_ushort(src[5 * GEMM_STAGE_PITCH]) << 16);
+                            o.w = (uint32_t)__half_as_ushort(src[6 * GEMM_STAGE_PITCH]) | ((uint32_t)__half_as_ushort(src[7 * GEMM_STAGE_PITCH]) << 16);
+                            __half* base = base0;
+                            int nn = nc;
                             if (grp > 0) {
-                                const int gi = n / grp;
+                                const int gi = nc / grp;
                                 base += (size_t)gi * grp_stride;
-                                nn = n - gi * grp;
+                                nn = nc - gi * grp;
                             }
-                            const bool lerp = (out_mode == OUT_LERP_A16);
-                            const float mu = lerp ? aux2[n] : 0.f;
-#pragma unroll
-                            for (int mt = 0; mt < MTE; ++mt) {
-                                float x0[16], x1[16];          // the lerp operands of a tile's 16 tokens are requested together
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const int m = mt * 16 + j;
-                                    const bool ok = lerp && m < mmax;
-                                    const size_t a_ = (size_t)m * ld_aux + n;
-                                    x0[j] = ok ? aux0[a_] : 0.f;
-                                    x1[j] = ok ? aux1[a_] : 0.f;
-                                }
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const int m = mt * 16 + j;
-                                    if (m < mmax) {
-                                        float y = apply_act(v[mt][j] + bias, ACT_C);
-                                        if (lerp) y = x0[j] + x1[j] * (mu + y);
-                                        base[a16_index(m, nn, ldo)] = f2h_sat(y);
-                                    }
-                                }
-                            }
-                        }
-                    };
-                    switch (act) {
-                        case ACT_TANH: body(std::integral_constant<int, ACT_TANH>{}); break;
-                        case ACT_SIGMOID: body(std::integral_constant<int, ACT_SIGMOID>{}); break;
-                        case ACT_SILU: body(std::integral_constant<int, ACT_SILU>{}); break;
-                        case ACT_RELU2: body(std::integral_constant<int, ACT_RELU2>{}); break;
-                        case ACT_EXPNEGEXP: body(std::integral_constant<int, ACT_EXPNEGEXP>{}); break;
-                        case ACT_V7DECAY: body(std::integral_constant<int, ACT_V7DECAY>{}); break;
-                        default: body(std::integral_constant<int, ACT_NONE>{}); break;
-                    }
-                } else {
-                    // one token tile (decode, and split operands after the hi + lo accumulators were added)
-                    if (out_mode == OUT_F32) {
-                        float* o = reinterpret_cast<float*>(outp) + n;
-#pragma unroll
-                        for (int m = 0; m < 16; ++m)             // straight from registers, all 16 stores in flight
-                            if (m < mmax) o[(size_t)m * ldo] = apply_act(v[0][m] + bias, act);
-                    } else {
-                        float lv[16];                            // dynamically indexed below: 64 bytes of local memory
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) lv[j] = v[0][j];
-                        __half* base = reinterpret_cast<__half*>(outp);
-                        int nn = n;
-                        if (grp > 0) {
-                            const int gi = n / grp;
-                            base += (size_t)gi * grp_stride;
-                            nn = n - gi * grp;
-                        }
-                        const float mu = (out_mode == OUT_LERP_A16) ? aux2[n] : 0.f;
-#pragma unroll 1
-                        for (int m0 = 0; m0 < mmax; m0 += 4) {
-                            // the two lerp operands of four tokens are requested together (L2 latency bound)
-                            float x0[4], x1[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const bool ok = (out_mode == OUT_LERP_A16) && (m0 + u < mmax);
-                                const size_t a_ = (size_t)(m0 + u) * ld_aux + n;
-                                x0[u] = ok ? aux0[a_] : 0.f;
-                                x1[u] = ok ? aux1[a_] : 0.f;
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const int m = m0 + u;
-                                if (m < mmax) {
-                                    float y = apply_act(lv[m] + bias, act);
-                                    if (out_mode == OUT_LERP_A16) y = x0[u] + x1[u] * (mu + y);
-                                    if (SPLIT) {
-                                        __half hi, lo;
-                                        split_h(y, hi, lo);
-                                        base[a16_index(m, nn, ldo)] = hi;
-                                        base[a16_index(m + 16, nn, ldo)] = lo;
-                                    } else {
-                                        base[a16_index(m, nn, ldo)] = f2h_sat(y);
-                                    }
-                                }
-                            }
+                            *reinterpret_cast<uint4*>(base + a16_index(mt * 16 + m + rowoff, nn, ldo)) = o;
                         }
                     }
+                    named_bar_sync(3, GEMM_EPI_THREADS);            // the staging buffer is rewritten by the next tile
+                };
+                auto body = [&](auto act_c) {
+                    constexpr int ACT_C = decltype(act_c)::value;
+#pragma unroll
+                    for (int mt = 0; mt < MTE; ++mt) {
+                        if (mt * 16 < mmax) {                           // uniform over the CTA
+                            float x0[16], x1[16];                       // the lerp operands of the tile's 16 tokens, requested together
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int m = mt * 16 + j;
+                                const bool ok = lerp && row_ok && m < mmax;
+                                const size_t a_ = (size_t)m * ld_aux + n;
+                                x0[j] = ok ? aux0[a_] : 0.f;
+                                x1[j] = ok ? aux1[a_] : 0.f;
+                            }
+                            __half hi[16], lo[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float y = apply_act(v[mt][j] + bias, ACT_C);
+                                if (lerp) y = x0[j] + x1[j] * (mu + y);
+                                if (!row_ok) y = 0.f;
+                                if (SPLIT) split_h(y, hi[j], lo[j]);
+                                else hi[j] = f2h_sat(y);
+                            }
+                            stage_and_store(mt, hi, 0);
+                            if (SPLIT) stage_and_store(mt, lo, 16);
+                        }
+                    }
+                };
+                switch (act) {
+                    case ACT_TANH: body(std::integral_constant<int, ACT_TANH>{}); break;
+                    case ACT_SIGMOID: body(std::integral_constant<int, ACT_SIGMOID>{}); break;
+                    case ACT_SILU: body(std::integral_constant<int, ACT_SILU>{}); break;
+                    case ACT_RELU2: body(std::integral_constant<int, ACT_RELU2>{}); break;
+                    case ACT_EXPNEGEXP: body(std::integral_constant<int, ACT_EXPNEGEXP>{}); break;
+                    case ACT_V7DECAY: body(std::integral_constant<int, ACT_V7DECAY>{}); break;
+                    default: body(std::integral_constant<int, ACT_NONE>{}); break;
                 }
             }
         }
@@ -429,6 +441,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, RING == 1 ? 2 : 1) gemm_kernel(c
     using Cfg = GemmCfg<MT, RING>;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ int s_last;
+    __shared__ __align__(16) __half s_stage[GEMM_EPI_THREADS * GEMM_STAGE_PITCH];     // A16 epilogue transpose (6 KB)
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_bar = smem_base + Cfg::NSTAGE * Cfg::STAGE_BYTES;
     const uint32_t empty_bar = full_bar + Cfg::NSTAGE * 8;
@@ -539,7 +552,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, RING == 1 ? 2 : 1) gemm_kernel(c
         pdl_wait();
         if (tid == 0) stamp(5);
         unsigned segcount = 0;
-        gemm_epilogue_role<MT, SPLIT>(p, cta, G, b0, b1, tfull_bar, tempty_bar, tmem_base, segcount, *p.nrows, &s_last, tr);
+        gemm_epilogue_role<MT, SPLIT>(p, cta, G, b0, b1, tfull_bar, tempty_bar, tmem_base, segcount, *p.nrows, &s_last, s_stage, tr);
         if (tid == 0) stamp(6);
     }
     tc_fence_before();
