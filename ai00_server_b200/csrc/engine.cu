@@ -422,6 +422,7 @@ struct b200rwkv_engine {
     uint8_t* comm_base = nullptr;
     size_t comm_bytes = 0, off_part_att = 0, off_part_ffn = 0, off_rr = 0, off_logits = 0, off_flags = 0;
     uint8_t* peer_base[8] = {nullptr};
+    bool peer_ipc[8] = {false};       // peer_base[q] was opened with cudaIpcOpenMemHandle (closed in the destructor)
     bool connected = false;
     TpBar tpbar;
     unsigned* d_epoch = nullptr;
@@ -546,6 +547,8 @@ b200rwkv_engine::~b200rwkv_engine() {
     cudaDeviceSynchronize();
     for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
     for (auto& kv : snaps) { cudaFree(kv.second.buf); if (kv.second.logits) cudaFree(kv.second.logits); }
+    for (int q = 0; q < 8; ++q)
+        if (peer_ipc[q] && peer_base[q]) cudaIpcCloseMemHandle(peer_base[q]);
     for (void* p : allocs) cudaFree(p);
     if (d_tmp) cudaFree(d_tmp);          // only still set when build() threw
     if (sm_in) cudaFree(sm_in);
@@ -1914,6 +1917,7 @@ int32_t b200rwkv_tp_connect(b200rwkv_engine* e, const uint8_t* handles) {
             void* p = nullptr;
             CK(cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess));
             e->peer_base[q] = (uint8_t*)p;
+            e->peer_ipc[q] = true;
         }
     }
     e->finalize_tp();
@@ -2565,6 +2569,12 @@ int32_t b200rwkv_debug_read(b200rwkv_engine* e, const char* name, float* out, si
     } catch (const Error& ex) {
         *errp_ = ex.what();
         return ex.code;
+    } catch (const std::exception& ex) {
+        *errp_ = ex.what();
+        return B200RWKV_ERR_INVALID;
+    } catch (...) {
+        *errp_ = "unknown exception";
+        return B200RWKV_ERR_INVALID;
     }
 }
 
