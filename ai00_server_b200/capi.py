@@ -36,7 +36,11 @@ class Options(C.Structure):
     """b200rwkv_options (include/b200rwkv.h)."""
     _fields_ = [("struct_bytes", C.c_uint32), ("max_batch", C.c_int32), ("token_chunk_size", C.c_int32), ("precision", C.c_int32),
                 ("num_devices", C.c_int32), ("devices", C.c_int32 * 8), ("num_lora", C.c_int32),
-                ("lora_st", C.c_void_p * MAX_LORA), ("lora_len", C.c_size_t * MAX_LORA), ("lora_alpha", C.c_float * MAX_LORA)]
+                ("lora_st", C.c_void_p * MAX_LORA), ("lora_len", C.c_size_t * MAX_LORA), ("lora_alpha", C.c_float * MAX_LORA),
+                ("quant_layers", C.c_int32), ("quant_type", C.c_int32)]
+
+
+QUANT_NONE, QUANT_INT8, QUANT_NF4 = 0, 1, 2
 
 
 class B200Error(RuntimeError):
@@ -76,6 +80,7 @@ SYMBOLS = [
     ("b200rwkv_bench_decode", C.c_int32, [_P, C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64), _P]),
     ("b200rwkv_profile_step", C.c_int32, [_P, C.c_int32, _P, _P, C.POINTER(C.c_float * 4), C.POINTER(C.c_int32 * 4), C.POINTER(C.c_int64)]),
     ("b200rwkv_profile_insitu", C.c_int32, [_P, C.c_int32, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.POINTER(C.c_double)]),
+    ("b200rwkv_op_quantize", C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     ("b200rwkv_op_wkv", C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [_P] * 14),
     ("b200rwkv_launch_count", C.c_int32, [_P, C.POINTER(C.c_int64)]),
     ("b200rwkv_keep_hidden", C.c_int32, [_P, C.c_int32]),
@@ -138,6 +143,19 @@ def info_from_st(st: np.ndarray) -> dict:
     out = Info()
     check(lib().b200rwkv_info_from_st(ptr(st), st.size, C.byref(out)))
     return out.as_dict()
+
+
+def op_quantize(quant_type: int, w16, device: int = 0):
+    """The load-time quantiser on one [N, K] f16 matrix (b200rwkv_op_quantize).  Int8: (codes u8 [N, K], min f16 [N, K/128],
+    scale f16 [N, K/128]); NF4: (level indices u8 [N, K], absmax f16 [N, K/64])."""
+    w16 = np.ascontiguousarray(w16, np.float16)
+    N, K = w16.shape
+    nb = K // (128 if quant_type == QUANT_INT8 else 64)
+    codes = np.empty((N, K), np.uint8)
+    p0 = np.empty((N, nb), np.float16)
+    p1 = np.empty((N, nb), np.float16)
+    check(lib().b200rwkv_op_quantize(device, quant_type, N, K, ptr(w16), ptr(codes), ptr(p0), ptr(p1) if quant_type == QUANT_INT8 else None))
+    return (codes, p0, p1) if quant_type == QUANT_INT8 else (codes, p0)
 
 
 def op_wkv(version: int, r, k, v, w, state, u=None, a=None, k_k=None, k_a=None, r_k=None, g=None, lnx_w=None, lnx_b=None, device: int = 0):

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "qgemm.cuh"
 #include "pre6.cuh"
 #include "sample.cuh"
 #include "misc.cuh"
@@ -347,7 +348,8 @@ struct GemmLaunch {
     int grid = 0;
     int grid_wide = 0;         // grid of steps with >= 64 tokens: whole tiles per CTA (see make_launch)
     int total_tiles = 0;
-    size_t weight_bytes = 0;   // algorithmic (unpadded) f16 weight bytes streamed
+    size_t weight_bytes = 0;   // algorithmic (unpadded) weight bytes streamed (f16, or codes + block parameters)
+    int qtype = QT_NONE;       // weight format of every segment of the launch (qgemm.cuh)
 };
 
 struct SegDesc {
@@ -504,7 +506,8 @@ struct b200rwkv_engine {
     const __half* upload_tmp(const StTensor& t);
     float* vec_f32(const StFile& st, const std::string& name, size_t off, size_t count, float scale = 1.f, float bias = 0.f);
     A16Buf a16_alloc(int K, int nmat = 1);
-    GemmLaunch make_launch(std::vector<SegDesc>& segs, int force_grid = 0);
+    GemmLaunch make_launch(std::vector<SegDesc>& segs, int force_grid = 0, int qtype = QT_NONE);
+    int quant_layers = 0, quant_type = QT_NONE;     // the first `quant_layers` layers hold Int8 / NF4 projection matrices
     int pick_split(int K, int tiles) const;
     void finalize_tp();
     template <typename P, typename... X>
@@ -665,10 +668,12 @@ A16Buf b200rwkv_engine::a16_alloc(int K, int nmat) {
     return b;
 }
 
-GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_grid) {
+GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_grid, int qtype) {
     REQUIRE(!segs.empty() && (int)segs.size() <= GEMM_MAX_SEG, B200RWKV_ERR_INVALID, "internal: bad segment count");
     GemmLaunch g;
     memset(&g.p, 0, sizeof(g.p));
+    g.qtype = qtype;
+    const size_t blk_bytes = (size_t)q_block_bytes(qtype);
     int blk = 0, tile = 0, kbmax = 0;
     for (size_t i = 0; i < segs.size(); ++i) {
         SegDesc& d = segs[i];
@@ -685,12 +690,19 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
         blk += sg.tiles * sg.KB;
         tile += sg.tiles;
         kbmax = std::max(kbmax, sg.KB);
-        g.weight_bytes += (size_t)d.N * d.K * 2;
+        if (qtype == QT_NONE) g.weight_bytes += (size_t)d.N * d.K * 2;
+        else {
+            // quantisation blocks are runs of 128 (Int8) / 64 (NF4) consecutive inputs of one output row of the FULL matrix
+            REQUIRE(d.K % GEMM_BK == 0 && d.k0 % GEMM_BK == 0, B200RWKV_ERR_UNSUPPORTED,
+                    "quantised projections need input dimensions that are multiples of 128");
+            g.weight_bytes += qtype == QT_INT8 ? (size_t)d.N * d.K + (size_t)d.N * (d.K / 128) * 4
+                                               : (size_t)d.N * d.K / 2 + (size_t)d.N * (d.K / 64) * 2;
+        }
     }
     g.p.nseg = (int)segs.size();
     g.p.total_blocks = blk;
     g.total_tiles = tile;
-    uint8_t* W = (uint8_t*)dalloc((size_t)blk * GEMM_WBYTES, false);
+    uint8_t* W = (uint8_t*)dalloc((size_t)blk * blk_bytes, false);
     g.p.W = W;
     for (size_t i = 0; i < segs.size(); ++i) {
         SegDesc& d = segs[i];
@@ -707,6 +719,16 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
             REQUIRE(t.shape.size() == 2, B200RWKV_ERR_INVALID, "internal: expected 2-D weight");
             ld = (int)t.shape[1];
             REQUIRE(d.n0 + d.N <= t.shape[0] && d.k0 + d.K <= t.shape[1], B200RWKV_ERR_INVALID, "weight shape mismatch");
+        }
+        if (qtype != QT_NONE) {
+            const size_t nwarp = (size_t)sg.tiles * sg.KB * GEMM_BN;
+            const int grid = (int)std::min<size_t>((nwarp + 7) / 8, 148 * 32);
+            uint8_t* dstq = W + (size_t)sg.blk_begin * blk_bytes;
+            if (qtype == QT_INT8) quantize_weight_kernel<QT_INT8><<<grid, 256>>>(src, ld, d.n0, d.k0, d.N, sg.tiles, sg.KB, dstq);
+            else quantize_weight_kernel<QT_NF4><<<grid, 256>>>(src, ld, d.n0, d.k0, d.N, sg.tiles, sg.KB, dstq);
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+            continue;
         }
         const size_t nchunk = (size_t)sg.tiles * sg.KB * (GEMM_WBYTES / 16);
         const int grid = (int)std::min<size_t>((nchunk + 255) / 256, 148 * 16);
@@ -788,6 +810,18 @@ void b200rwkv_engine::launch_k(void (*kern)(P, X...), dim3 grid, dim3 block, siz
 }
 
 void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, Profiler* prof, bool split) {
+    if (g.qtype != QT_NONE) {
+        REQUIRE(!split, B200RWKV_ERR_UNSUPPORTED, "internal: quantised projections run with f16 activations");
+        const int grid = MT >= 4 ? g.grid_wide : g.grid;
+#define QLAUNCH(MT_, QT_) launch_k(qgemm_kernel<MT_, QT_>, dim3(grid), dim3(QGEMM_THREADS), QGemmCfg<MT_, QT_>::SMEM_BYTES, g.p, KC_GEMM, s, prof)
+        if (g.qtype == QT_INT8) {
+            switch (MT) { case 1: QLAUNCH(1, QT_INT8); break; case 2: QLAUNCH(2, QT_INT8); break; case 4: QLAUNCH(4, QT_INT8); break; default: QLAUNCH(8, QT_INT8); break; }
+        } else {
+            switch (MT) { case 1: QLAUNCH(1, QT_NF4); break; case 2: QLAUNCH(2, QT_NF4); break; case 4: QLAUNCH(4, QT_NF4); break; default: QLAUNCH(8, QT_NF4); break; }
+        }
+#undef QLAUNCH
+        return;
+    }
     // RING 2 = one stage less than fits, so the small kernels around a projection can share its SMs (findings r1 §7)
     switch (MT) {
         case 1:
@@ -836,6 +870,15 @@ void b200rwkv_engine::build(const StFile& st) {
     CK(cudaFuncSetAttribute(gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<4>::SMEM_BYTES));
     CK(cudaFuncSetAttribute(gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<8>::SMEM_BYTES));
+    if (quant_layers > 0 && quant_type != QT_NONE) {
+        REQUIRE(quant_type == QT_INT8 || quant_type == QT_NF4, B200RWKV_ERR_UNSUPPORTED, "quant_type must be Int8 or NF4 (SF4 is not implemented)");
+        REQUIRE(world == 1, B200RWKV_ERR_UNSUPPORTED, "quantised layers are single-GPU in this version");
+        REQUIRE(precision == 0, B200RWKV_ERR_UNSUPPORTED, "quantised layers run with precision 0 (f16 operands)");
+#define QATTR(MT_, QT_) CK(cudaFuncSetAttribute(qgemm_kernel<MT_, QT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, QGemmCfg<MT_, QT_>::SMEM_BYTES))
+        QATTR(1, QT_INT8); QATTR(2, QT_INT8); QATTR(4, QT_INT8); QATTR(8, QT_INT8);
+        QATTR(1, QT_NF4); QATTR(2, QT_NF4); QATTR(4, QT_NF4); QATTR(8, QT_NF4);
+#undef QATTR
+    }
     {   // prefill steps of up to 128 tokens: per-token decay rows of a slot live in dynamic shared memory
         const int wkv_smem_max = 96 * 1024;
         CK(cudaFuncSetAttribute(wkv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, wkv_smem_max));
@@ -959,6 +1002,9 @@ void b200rwkv_engine::build(const StFile& st) {
         const std::string a = b + "att.", f = b + "ffn.";
         float* att_sh = att_shift + (size_t)l * S * C;
         float* ffn_sh = ffn_shift + (size_t)l * S * C;
+        // `quant`: the eight projection matrices of the first layers are quantised, adapters / LoRA matrices stay f16 -- so a
+        // launch that mixed both kinds (R/K/V/G + decay LoRA, v7 R/K/V + adapters) goes out as two in those layers
+        const int lq = (l < quant_layers) ? quant_type : QT_NONE;
 
         // ---------------- LN1 (+ residual update from the previous layer's channel mix) ----------------
         LnMixParams& n1 = ly.ln1;
@@ -1053,6 +1099,10 @@ void b200rwkv_engine::build(const StFile& st) {
                 sv.push_back(f32_seg(Wk, c0, Cl, 0, C, a_x[1], f_k, Cl, ACT_NONE, nullptr));
                 sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[2], f_v, Cl, ACT_NONE, nullptr));
                 sv.push_back(f32_seg(st.get(a + "gate.weight"), c0, Cl, 0, C, a_x[4], f_g, Cl, ACT_SILU, nullptr));
+                if (lq != QT_NONE) {
+                    ly.pre.push_back(make_launch(sv, 0, lq));
+                    sv.clear();
+                }
                 sv.push_back(a16_seg(st.get(a + "time_decay_w1"), 0, Dd, 0, C, a_x[0], a_lora[1], ACT_TANH, nullptr));
                 ly.pre.push_back(make_launch(sv));
             }
@@ -1097,7 +1147,7 @@ void b200rwkv_engine::build(const StFile& st) {
             sv.push_back(f32_seg(Wk, c0, Cl, 0, C, a_x[1], f_k, Cl, ACT_NONE, nullptr));
             sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[2], f_v, Cl, ACT_NONE, nullptr));
             sv.push_back(f32_seg(st.get(a + "gate.weight"), c0, Cl, 0, C, a_x[4], f_g, Cl, ACT_SILU, nullptr));
-            ly.pre.push_back(make_launch(sv));
+            ly.pre.push_back(make_launch(sv, 0, lq));
             {
                 const StTensor& td = st.get(a + "time_decay");
                 REQUIRE(td.numel() == C, B200RWKV_ERR_UNSUPPORTED, "v5 time_decay must be [H, N]");
@@ -1128,6 +1178,10 @@ void b200rwkv_engine::build(const StFile& st) {
                 sv.push_back(f32_seg(Wr, c0, Cl, 0, C, a_x[0], f_r, Cl, ACT_NONE, nullptr));
                 sv.push_back(f32_seg(Wk, c0, Cl, 0, C, a_x[2], f_k, Cl, ACT_NONE, nullptr));
                 sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[3], f_v, Cl, ACT_NONE, nullptr));
+                if (lq != QT_NONE) {
+                    ly.pre.push_back(make_launch(sv, 0, lq));
+                    sv.clear();
+                }
                 sv.push_back(a16_seg(st.get(a + "w1"), 0, Dw, 0, C, a_x[1], a_lora[0], ACT_TANH, nullptr));
                 sv.push_back(a16_seg(st.get(a + "a1"), 0, Da, 0, C, a_x[4], a_lora[1], ACT_NONE, nullptr));
                 if (l > 0) sv.push_back(a16_seg(st.get(a + "v1"), 0, Dv, 0, C, a_x[3], a_lora[2], ACT_NONE, nullptr));
@@ -1157,7 +1211,7 @@ void b200rwkv_engine::build(const StFile& st) {
             for (int sp = 0; sp < S_att; ++sp)
                 sv.push_back(f32_seg(Wo, 0, C, c0 + sp * (Cl / S_att), Cl / S_att, a_out, part_att + (size_t)sp * TC, C, ACT_NONE,
                                      nullptr, sp * (Cl / S_att)));
-            ly.o = make_launch(sv, S_att > 1 ? cdiv(C, GEMM_BN) * S_att : 0);
+            ly.o = make_launch(sv, S_att > 1 ? cdiv(C, GEMM_BN) * S_att : 0, lq);
         }
 
         // ---------------- LN2 ----------------
@@ -1179,7 +1233,7 @@ void b200rwkv_engine::build(const StFile& st) {
             n2.mix_out[0] = a_x[0].p;
             std::vector<SegDesc> sv;
             sv.push_back(a16_seg(Fk, f0, Fl, 0, C, a_x[0], a_kk, ACT_RELU2, nullptr));
-            ly.ffn.push_back(make_launch(sv));
+            ly.ffn.push_back(make_launch(sv, 0, lq));
         } else {
             n2.n_mix = 2;
             if (ver == 6) {
@@ -1194,14 +1248,14 @@ void b200rwkv_engine::build(const StFile& st) {
             std::vector<SegDesc> sv;
             sv.push_back(a16_seg(Fk, f0, Fl, 0, C, a_x[0], a_kk, ACT_RELU2, nullptr));
             sv.push_back(f32_seg(st.get(f + "receptance.weight"), c0, Cl, 0, C, a_x[1], f_rr, Cl, ACT_SIGMOID, nullptr));
-            ly.ffn.push_back(make_launch(sv));
+            ly.ffn.push_back(make_launch(sv, 0, lq));
         }
         {
             std::vector<SegDesc> sv;
             for (int sp = 0; sp < S_ffn; ++sp)
                 sv.push_back(f32_seg(Fv, 0, C, f0 + sp * (Fl / S_ffn), Fl / S_ffn, a_kk, part_ffn + (size_t)sp * TC, C, ACT_NONE,
                                      nullptr, sp * (Fl / S_ffn)));
-            ly.ffn.push_back(make_launch(sv, S_ffn > 1 ? cdiv(C, GEMM_BN) * S_ffn : 0));
+            ly.ffn.push_back(make_launch(sv, S_ffn > 1 ? cdiv(C, GEMM_BN) * S_ffn : 0, lq));
         }
     }
 
@@ -1316,7 +1370,7 @@ void b200rwkv_engine::enqueue_step(cudaStream_t s, int MT, int MTR, Profiler* pr
             REQUIRE(seq_pos < seq.size() && seq[seq_pos] == &g, B200RWKV_ERR_INVALID, "internal: projection launch order");
             const GemmLaunch& nx = *seq[(seq_pos + 1) % seq.size()];
             ++seq_pos;
-            g2.p.next_W = nx.p.W;
+            g2.p.next_W = nx.qtype == QT_NONE ? nx.p.W : nullptr;     // the L2 prefetch walks 32 KB f16 blocks
             g2.p.next_blocks = nx.p.total_blocks;
             g2.p.next_grid = mt >= 4 ? nx.grid_wide : nx.grid;
             g2.p.prefetch_blocks = prefetch_blocks;
@@ -1826,7 +1880,8 @@ int32_t b200rwkv_info_from_st(const uint8_t* st, size_t len, b200rwkv_info* out)
 struct LoraArg { const uint8_t* st; size_t len; float alpha; };
 
 static int32_t create_rank(const uint8_t* st, size_t len, int32_t device, int32_t max_batch, int32_t token_chunk_size,
-                           int32_t precision, int32_t rank, int32_t world, const std::vector<LoraArg>& lora, b200rwkv_engine** out) {
+                           int32_t precision, int32_t rank, int32_t world, const std::vector<LoraArg>& lora, b200rwkv_engine** out,
+                           int32_t quant_layers = 0, int32_t quant_type = 0) {
     API_BEGIN((b200rwkv_engine*)nullptr)
     REQUIRE(out, B200RWKV_ERR_INVALID, "null out");
     *out = nullptr;
@@ -1860,6 +1915,9 @@ static int32_t create_rank(const uint8_t* st, size_t len, int32_t device, int32_
     }
     e->dev = device; e->rank = rank; e->world = world; e->num_sms = prop.multiProcessorCount;
     e->S = max_batch; e->chunk = token_chunk_size; e->precision = precision;
+    REQUIRE(quant_layers >= 0 && quant_type >= 0, B200RWKV_ERR_INVALID, "bad quant_layers / quant_type");
+    e->quant_layers = quant_type == QT_NONE ? 0 : quant_layers;
+    e->quant_type = quant_layers == 0 ? (int)QT_NONE : quant_type;
     if (const char* v = dbg_env("B200RWKV_GRAPH")) e->use_graph = atoi(v) != 0;
     if (const char* v = dbg_env("B200RWKV_PDL")) e->use_pdl = atoi(v) != 0;
     e->build(f);
@@ -2412,6 +2470,52 @@ static int32_t rank_profile_insitu(b200rwkv_engine* e, int32_t nslot, const int3
     API_END
 }
 
+// Operator-level entry for the parity tests: the load-time quantiser (qgemm.cuh) on one matrix, un-tiled on the host into plain
+// row-major codes and per-block parameters so that oracle/quant_numpy.py can be compared bit for bit.
+int32_t b200rwkv_op_quantize(int32_t device, int32_t quant_type, int32_t N, int32_t K, const uint16_t* w_f16, uint8_t* codes,
+                             uint16_t* p0, uint16_t* p1) {
+    API_BEGIN((b200rwkv_engine*)nullptr)
+    REQUIRE(quant_type == QT_INT8 || quant_type == QT_NF4, B200RWKV_ERR_UNSUPPORTED, "quant_type must be Int8 or NF4");
+    REQUIRE(N >= 1 && K >= GEMM_BK && K % GEMM_BK == 0 && (size_t)N * K <= ((size_t)1 << 31) && w_f16 && codes && p0, B200RWKV_ERR_INVALID, "bad argument");
+    REQUIRE(quant_type == QT_NF4 || p1, B200RWKV_ERR_INVALID, "Int8 needs p1 (scales)");
+    CK(cudaSetDevice(device));
+    const int tiles = cdiv(N, GEMM_BN), KB = K / GEMM_BK;
+    const size_t blk = (size_t)q_block_bytes(quant_type), total = (size_t)tiles * KB * blk;
+    DevTmp src((size_t)N * K * 2), dst(total);
+    CK(cudaMemcpy(src.p, w_f16, (size_t)N * K * 2, cudaMemcpyHostToDevice));
+    const size_t nwarp = (size_t)tiles * KB * GEMM_BN;
+    const int grid = (int)std::min<size_t>((nwarp + 7) / 8, 148 * 32);
+    if (quant_type == QT_INT8) quantize_weight_kernel<QT_INT8><<<grid, 256>>>((const __half*)src.p, K, 0, 0, N, tiles, KB, (uint8_t*)dst.p);
+    else quantize_weight_kernel<QT_NF4><<<grid, 256>>>((const __half*)src.p, K, 0, 0, N, tiles, KB, (uint8_t*)dst.p);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    std::vector<uint8_t> h(total);
+    CK(cudaMemcpy(h.data(), dst.p, total, cudaMemcpyDeviceToHost));
+    for (int n = 0; n < N; ++n) {
+        const int tile = n / GEMM_BN, r = n % GEMM_BN;
+        for (int kb = 0; kb < KB; ++kb) {
+            const uint8_t* b = h.data() + ((size_t)tile * KB + kb) * blk;
+            if (quant_type == QT_INT8) {
+                for (int k = 0; k < GEMM_BK; ++k) codes[(size_t)n * K + kb * GEMM_BK + k] = b[(size_t)((k >> 4) * GEMM_BN + r) * 16 + (k & 15)];
+                uint16_t pr[2];
+                memcpy(pr, b + GEMM_BN * GEMM_BK + r * 4, 4);
+                p1[(size_t)n * KB + kb] = pr[0];      // scale
+                p0[(size_t)n * KB + kb] = pr[1];      // min
+            } else {
+                for (int k = 0; k < GEMM_BK; ++k) {
+                    const uint8_t by = b[(size_t)((k >> 5) * GEMM_BN + r) * 16 + ((k & 31) >> 1)];
+                    codes[(size_t)n * K + kb * GEMM_BK + k] = (k & 1) ? (by >> 4) : (by & 15);
+                }
+                uint16_t pr[2];
+                memcpy(pr, b + GEMM_BN * GEMM_BK / 2 + r * 4, 4);
+                p0[(size_t)n * (2 * KB) + 2 * kb] = pr[0];
+                p0[(size_t)n * (2 * KB) + 2 * kb + 1] = pr[1];
+            }
+        }
+    }
+    API_END
+}
+
 // Operator-level entry for the parity tests: ONE launch of the WKV kernel (recurrence + GroupNorm + bonus + gate) on caller
 // supplied head vectors and state, no model around it.  This is how the committed fla fixtures (tests/golden/wkv6_fla.npz,
 // wkv7_fla.npz: independent pins of the recurrences) reach the CUDA kernels.
@@ -2857,7 +2961,9 @@ int32_t b200rwkv_create_ex(const uint8_t* st, size_t len, const b200rwkv_options
     std::vector<LoraArg> lora;
     for (int i = 0; i < opt->num_lora; ++i) lora.push_back({opt->lora_st[i], opt->lora_len[i], opt->lora_alpha[i]});
     const int dev0 = opt->num_devices <= 0 ? 0 : opt->devices[0];
-    if (world == 1) return create_rank(st, len, dev0, opt->max_batch, opt->token_chunk_size, opt->precision, 0, 1, lora, out);
+    if (world == 1)
+        return create_rank(st, len, dev0, opt->max_batch, opt->token_chunk_size, opt->precision, 0, 1, lora, out, opt->quant_layers, opt->quant_type);
+    if (opt->quant_layers > 0 && opt->quant_type != B200RWKV_QUANT_NONE) { g_err = "quantised layers are single-GPU in this version"; return B200RWKV_ERR_UNSUPPORTED; }
     for (int r = 0; r < world; ++r)
         for (int q = 0; q < r; ++q)
             if (opt->devices[r] == opt->devices[q]) { g_err = "devices must be distinct"; return B200RWKV_ERR_INVALID; }

@@ -225,18 +225,26 @@ class Model:
     `TokioRuntime::new(bundle)`, lib.rs:484-497)."""
 
     def __init__(self, st: np.ndarray, max_batch: int = 8, token_chunk_size: int = 128, device: int = 0,
-                 precision: int = 0, rank: int = 0, world: int = 1, exact: bool = False, devices=None, lora=None):
+                 precision: int = 0, rank: int = 0, world: int = 1, exact: bool = False, devices=None, lora=None,
+                 quant: int = 0, quant_type: int | str = 0):
         """devices: list of CUDA ordinals -> ONE engine object owning all tensor-parallel ranks (b200rwkv_create_ex);
         lora: list of (st_bytes, alpha) blended at load (reference lib.rs:466-485);
+        quant / quant_type: the reload request's fields (lib.rs:211-215): the first `quant` layers in "Int8" or "NF4";
         rank / world: one process per GPU instead (b200rwkv_create_tp + tp.connect)."""
+        if isinstance(quant_type, str):
+            kinds = {"none": capi.QUANT_NONE, "int8": capi.QUANT_INT8, "nf4": capi.QUANT_NF4, "sf4": 3}
+            if quant_type.lower() not in kinds:
+                raise capi.B200Error(capi.ERR_INVALID, "quant_type must be None, Int8, NF4 or SF4")
+            quant_type = kinds[quant_type.lower()]
+        quantised = quant > 0 and quant_type != capi.QUANT_NONE
         if exact:
             precision = 1          # `Bundle::<f32>`: f32-exact activations (split hi + lo f16 operands)
         st = np.ascontiguousarray(st, dtype=np.uint8)
         h = C.c_void_p()
         L = capi.lib()
-        if devices is not None or lora:
+        if devices is not None or lora or quantised:
             if world != 1:
-                raise capi.B200Error(capi.ERR_INVALID, "devices / lora go through b200rwkv_create_ex (in-process ranks)")
+                raise capi.B200Error(capi.ERR_INVALID, "devices / lora / quant go through b200rwkv_create_ex (in-process ranks)")
             opt = capi.Options()
             opt.struct_bytes = C.sizeof(capi.Options)
             opt.max_batch, opt.token_chunk_size, opt.precision = max_batch, token_chunk_size, precision
@@ -250,6 +258,7 @@ class Model:
                 self._lora_keep.append(img)
                 opt.lora_st[i], opt.lora_len[i], opt.lora_alpha[i] = img.ctypes.data, img.size, float(alpha)
             opt.num_lora = len(lora or [])
+            opt.quant_layers, opt.quant_type = (int(quant), int(quant_type)) if quantised else (0, 0)
             capi.check(L.b200rwkv_create_ex(capi.ptr(st), st.size, C.byref(opt), C.byref(h)))
             self._lora_keep = []
         else:

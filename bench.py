@@ -293,12 +293,18 @@ def main():
     ap.add_argument("--exact", action="store_true", help="precision 1: f32-exact activations (split hi+lo operands)")
     ap.add_argument("--mode", default="decode", choices=["decode", "prefill"],
                     help="prefill = BASELINE.json configs[4]: the embeddings route's workload (prompts in, final states out)")
+    ap.add_argument("--quant", default="none", choices=["none", "int8", "nf4"],
+                    help="weight-only quantised projection matrices (the reference's quant_type); not the headline configuration")
+    ap.add_argument("--quant-layers", type=int, default=-1, help="the reference's `quant`: first N layers (default: all)")
     ap.add_argument("--seqs", type=int, default=256)
     ap.add_argument("--seq-len", type=int, default=512)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     PRESET, BATCH = args.preset, args.batch
     METRIC = metric_name(PRESET, BATCH)
+    if args.quant != "none":
+        METRIC = METRIC.replace("fp16", {"int8": "Int8", "nf4": "NF4"}[args.quant] + " projections (fp16 elsewhere)")
+        assert args.mode == "decode" and not args.exact and args.impl == "b200" and args.gpus == 1, "--quant: 1-GPU decode arm only"
     if args.mode == "prefill":
         return prefill_main(args)
 
@@ -344,7 +350,12 @@ def main():
 
     t_build = time.perf_counter()
     st = synth.make_st(shape, 0)
-    model = runtime.Model(st, max_batch=BATCH, token_chunk_size=64, device=dev, rank=rank, world=world, exact=args.exact)
+    qlayers = shape.L if args.quant_layers < 0 else min(args.quant_layers, shape.L)
+    if args.quant != "none":
+        model = runtime.Model(st, max_batch=BATCH, token_chunk_size=64, device=dev, quant=qlayers, quant_type=args.quant)
+        config["weights"] = f"first {qlayers} of {shape.L} layers: eight projection matrices in {args.quant} (quantised at load on the GPU)"
+    else:
+        model = runtime.Model(st, max_batch=BATCH, token_chunk_size=64, device=dev, rank=rank, world=world, exact=args.exact)
     if world > 1:
         from ai00_server_b200 import tp
         tp.connect(model)
@@ -461,9 +472,14 @@ def main():
     gemm_us, gemm_n, gemm_bytes = cls["gemm"]
     gemm_gbs = gemm_bytes / (gemm_us * 1e-6) / 1e9 if gemm_us > 0 else 0.0
     alg_bytes = synth.algorithmic_bytes_per_step(shape, BATCH) / world
+    if args.quant != "none":
+        C_, F_ = shape.C, shape.F
+        mats = ([(C_, C_)] * (5 if shape.version != 7 else 4)) + [(F_, C_), (C_, F_)] + ([(C_, C_)] if shape.version != 7 else [])
+        per = (lambda n, k: n * k + n * k // 128 * 4) if args.quant == "int8" else (lambda n, k: n * k // 2 + n * k // 64 * 2)
+        alg_bytes += qlayers * sum(per(n, k) - 2 * n * k for n, k in mats)
     traffic = None       # DRAM bytes of the same launches from the committed ncu capture (N = 1 capture of this workload)
     tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if world == 1 and PRESET == "v6-7b" and BATCH == 16 and os.path.exists(tpath):
+    if world == 1 and PRESET == "v6-7b" and BATCH == 16 and args.quant == "none" and os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic = tj["layers"] * sum(x["dram_bytes"] for x in tj["per_layer_gemm_launches"]) + tj["head"]["algorithmic_weight_bytes"]
     windows_sum_us = sum(v[0] for v in cls.values())
@@ -492,7 +508,7 @@ def main():
 
     # ---- the parity path beside the throughput path: precision 1 (f32-exact activations) on the same workload ----
     exact_rec = None
-    if world == 1 and not args.exact and os.environ.get("B200RWKV_BENCH_SKIP_EXACT") != "1":
+    if world == 1 and not args.exact and args.quant == "none" and os.environ.get("B200RWKV_BENCH_SKIP_EXACT") != "1":
         m2 = runtime.Model(st, max_batch=BATCH, token_chunk_size=64, device=dev, exact=True)
         for s_ in slots:
             m2.state.load(zero, s_)
@@ -505,7 +521,7 @@ def main():
 
     # ---- cpu baseline (rank 0, N=1 only) ----
     cpu = None
-    if world == 1 and args.cpu_steps > 0:
+    if world == 1 and args.cpu_steps > 0 and args.quant == "none":
         w = O.parse_st(st)
         ctoks = toks[:, PROMPT:PROMPT + args.cpu_steps + 1]
         tps, cms, threads, _ = cpu_arm(w, BATCH, args.cpu_steps, 1, ctoks, budget_s=30.0)

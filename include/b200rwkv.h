@@ -96,7 +96,15 @@ typedef struct {
     const uint8_t* lora_st[B200RWKV_MAX_LORA];
     size_t lora_len[B200RWKV_MAX_LORA];
     float lora_alpha[B200RWKV_MAX_LORA];
+    /* `quant` / `quant_type` of the reload request (lib.rs:211-215, 465: the first `quant_layers` layers keep their eight
+     * projection matrices in a weight-only quantised format; everything else stays f16).  Single GPU, precision 0 only. */
+    int32_t quant_layers;
+    int32_t quant_type;               /* B200RWKV_QUANT_* */
 } b200rwkv_options;
+#define B200RWKV_QUANT_NONE 0
+#define B200RWKV_QUANT_INT8 1         /* blocks of 128 inputs: f16 (min, max) + 8-bit codes */
+#define B200RWKV_QUANT_NF4 2          /* blocks of 64 inputs: f16 absmax + 4-bit NormalFloat codes */
+                                      /* Quant::SF4 is not implemented: create_ex answers B200RWKV_ERR_UNSUPPORTED */
 int32_t b200rwkv_create_ex(const uint8_t* st, size_t len, const b200rwkv_options* opt, b200rwkv_engine** out);
 
 /* Tensor-parallel construction, one process per GPU (head / column parallel).
@@ -225,6 +233,13 @@ int32_t b200rwkv_profile_insitu(b200rwkv_engine*, int32_t nslot, const int32_t* 
  * lnx_w / lnx_b [H*64] (NULL = 1 / 0); state: in/out [H][64][64] in the device orientation M[value][key] (v5/v6: the
  * transpose of S[key][value]); out: [T, H*64], the f16 values the kernel hands to the output projection.  The committed
  * flash-linear-attention fixtures (tests/golden/wkv6_fla.npz, wkv7_fla.npz) are checked through this entry. */
+/* Operator-level entry (parity tests): the load-time quantiser on a caller-supplied row-major f16 matrix [N, K] (K % 128 == 0),
+ * returned in plain order: codes [N, K] (one byte per element: Int8 code, or NF4 level index 0..15), p0 [N, K/block] (Int8: block
+ * minimum, NF4: block absmax), p1 [N, K/block] (Int8: the scale f16((max - min) / 255); NF4: unused, may be NULL).  p0 / p1 are f16
+ * bit patterns.  block = 128 (Int8) or 64 (NF4). */
+int32_t b200rwkv_op_quantize(int32_t device, int32_t quant_type, int32_t N, int32_t K, const uint16_t* w_f16, uint8_t* codes,
+                             uint16_t* p0, uint16_t* p1);
+
 int32_t b200rwkv_op_wkv(int32_t device, int32_t version, int32_t T, int32_t H, const float* r, const float* k, const float* v,
                         const float* w, const float* u, const float* a, const float* k_k, const float* k_a, const float* r_k,
                         const float* g, const float* lnx_w, const float* lnx_b, float* state, float* out);
