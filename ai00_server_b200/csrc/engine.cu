@@ -508,6 +508,7 @@ struct b200rwkv_engine {
     A16Buf a16_alloc(int K, int nmat = 1);
     GemmLaunch make_launch(std::vector<SegDesc>& segs, int force_grid = 0, int qtype = QT_NONE);
     int quant_layers = 0, quant_type = QT_NONE;     // the first `quant_layers` layers hold Int8 / NF4 projection matrices
+    bool q_ts = true;                               // expanded weights go to tensor memory (qgemm.cuh); false = reference variant
     int pick_split(int K, int tiles) const;
     void finalize_tp();
     template <typename P, typename... X>
@@ -673,6 +674,8 @@ GemmLaunch b200rwkv_engine::make_launch(std::vector<SegDesc>& segs, int force_gr
     GemmLaunch g;
     memset(&g.p, 0, sizeof(g.p));
     g.qtype = qtype;
+    g.p.qvar = 1;
+    if (const char* v = dbg_env("B200RWKV_QVAR")) g.p.qvar = atoi(v);
     const size_t blk_bytes = (size_t)q_block_bytes(qtype);
     int blk = 0, tile = 0, kbmax = 0;
     for (size_t i = 0; i < segs.size(); ++i) {
@@ -813,8 +816,11 @@ void b200rwkv_engine::launch_gemm(const GemmLaunch& g, int MT, cudaStream_t s, P
     if (g.qtype != QT_NONE) {
         REQUIRE(!split, B200RWKV_ERR_UNSUPPORTED, "internal: quantised projections run with f16 activations");
         const int grid = MT >= 4 ? g.grid_wide : g.grid;
-#define QLAUNCH(MT_, QT_) launch_k(qgemm_kernel<MT_, QT_>, dim3(grid), dim3(QGEMM_THREADS), QGemmCfg<MT_, QT_>::SMEM_BYTES, g.p, KC_GEMM, s, prof)
-        if (g.qtype == QT_INT8) {
+#define QLAUNCH(MT_, QT_) launch_k(qgemm_kernel<MT_, QT_, true>, dim3(grid), dim3(QGEMM_THREADS), QGemmCfg<MT_, QT_, true>::SMEM_BYTES, g.p, KC_GEMM, s, prof)
+        if (!q_ts && MT == 1) {      // reference variant (expanded weights through shared memory), decode shape only
+            if (g.qtype == QT_INT8) launch_k(qgemm_kernel<1, QT_INT8, false>, dim3(grid), dim3(QGEMM_THREADS), QGemmCfg<1, QT_INT8, false>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+            else launch_k(qgemm_kernel<1, QT_NF4, false>, dim3(grid), dim3(QGEMM_THREADS), QGemmCfg<1, QT_NF4, false>::SMEM_BYTES, g.p, KC_GEMM, s, prof);
+        } else if (g.qtype == QT_INT8) {
             switch (MT) { case 1: QLAUNCH(1, QT_INT8); break; case 2: QLAUNCH(2, QT_INT8); break; case 4: QLAUNCH(4, QT_INT8); break; default: QLAUNCH(8, QT_INT8); break; }
         } else {
             switch (MT) { case 1: QLAUNCH(1, QT_NF4); break; case 2: QLAUNCH(2, QT_NF4); break; case 4: QLAUNCH(4, QT_NF4); break; default: QLAUNCH(8, QT_NF4); break; }
@@ -874,9 +880,12 @@ void b200rwkv_engine::build(const StFile& st) {
         REQUIRE(quant_type == QT_INT8 || quant_type == QT_NF4, B200RWKV_ERR_UNSUPPORTED, "quant_type must be Int8 or NF4 (SF4 is not implemented)");
         REQUIRE(world == 1, B200RWKV_ERR_UNSUPPORTED, "quantised layers are single-GPU in this version");
         REQUIRE(precision == 0, B200RWKV_ERR_UNSUPPORTED, "quantised layers run with precision 0 (f16 operands)");
-#define QATTR(MT_, QT_) CK(cudaFuncSetAttribute(qgemm_kernel<MT_, QT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, QGemmCfg<MT_, QT_>::SMEM_BYTES))
+#define QATTR(MT_, QT_) CK(cudaFuncSetAttribute(qgemm_kernel<MT_, QT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QGemmCfg<MT_, QT_, true>::SMEM_BYTES))
         QATTR(1, QT_INT8); QATTR(2, QT_INT8); QATTR(4, QT_INT8); QATTR(8, QT_INT8);
         QATTR(1, QT_NF4); QATTR(2, QT_NF4); QATTR(4, QT_NF4); QATTR(8, QT_NF4);
+        CK(cudaFuncSetAttribute(qgemm_kernel<1, QT_INT8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QGemmCfg<1, QT_INT8, false>::SMEM_BYTES));
+        CK(cudaFuncSetAttribute(qgemm_kernel<1, QT_NF4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QGemmCfg<1, QT_NF4, false>::SMEM_BYTES));
+        if (const char* v = dbg_env("B200RWKV_QTS")) q_ts = atoi(v) != 0;
 #undef QATTR
     }
     {   // prefill steps of up to 128 tokens: per-token decay rows of a slot live in dynamic shared memory
@@ -1100,11 +1109,16 @@ void b200rwkv_engine::build(const StFile& st) {
                 sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[2], f_v, Cl, ACT_NONE, nullptr));
                 sv.push_back(f32_seg(st.get(a + "gate.weight"), c0, Cl, 0, C, a_x[4], f_g, Cl, ACT_SILU, nullptr));
                 if (lq != QT_NONE) {
+                    // the small f16 launch goes first: it occupies a handful of SMs, and behind it the quantised launch is
+                    // already resident on the others filling its ring (programmatic dependent launch)
+                    std::vector<SegDesc> sd;
+                    sd.push_back(a16_seg(st.get(a + "time_decay_w1"), 0, Dd, 0, C, a_x[0], a_lora[1], ACT_TANH, nullptr));
+                    ly.pre.push_back(make_launch(sd));
                     ly.pre.push_back(make_launch(sv, 0, lq));
-                    sv.clear();
+                } else {
+                    sv.push_back(a16_seg(st.get(a + "time_decay_w1"), 0, Dd, 0, C, a_x[0], a_lora[1], ACT_TANH, nullptr));
+                    ly.pre.push_back(make_launch(sv));
                 }
-                sv.push_back(a16_seg(st.get(a + "time_decay_w1"), 0, Dd, 0, C, a_x[0], a_lora[1], ACT_TANH, nullptr));
-                ly.pre.push_back(make_launch(sv));
             }
             // decay LoRA stage 2: w = exp(-exp(time_decay + Wd2 d))
             {
@@ -1178,15 +1192,14 @@ void b200rwkv_engine::build(const StFile& st) {
                 sv.push_back(f32_seg(Wr, c0, Cl, 0, C, a_x[0], f_r, Cl, ACT_NONE, nullptr));
                 sv.push_back(f32_seg(Wk, c0, Cl, 0, C, a_x[2], f_k, Cl, ACT_NONE, nullptr));
                 sv.push_back(f32_seg(Wv, c0, Cl, 0, C, a_x[3], f_v, Cl, ACT_NONE, nullptr));
-                if (lq != QT_NONE) {
-                    ly.pre.push_back(make_launch(sv, 0, lq));
-                    sv.clear();
-                }
+                std::vector<SegDesc> sq;
+                if (lq != QT_NONE) sq.swap(sv);          // quantised R/K/V go out as their own launch, after the f16 adapters
                 sv.push_back(a16_seg(st.get(a + "w1"), 0, Dw, 0, C, a_x[1], a_lora[0], ACT_TANH, nullptr));
                 sv.push_back(a16_seg(st.get(a + "a1"), 0, Da, 0, C, a_x[4], a_lora[1], ACT_NONE, nullptr));
                 if (l > 0) sv.push_back(a16_seg(st.get(a + "v1"), 0, Dv, 0, C, a_x[3], a_lora[2], ACT_NONE, nullptr));
                 sv.push_back(a16_seg(st.get(a + "g1"), 0, Dg, 0, C, a_x[5], a_lora[3], ACT_SIGMOID, nullptr));
                 ly.pre.push_back(make_launch(sv));
+                if (lq != QT_NONE) ly.pre.push_back(make_launch(sq, 0, lq));
             }
             {
                 std::vector<SegDesc> sv;

@@ -94,6 +94,7 @@ struct GemmParams {
     // that launch, so HBM keeps working through this launch's tail, the launch boundary and any small kernel between
     const uint8_t* next_W;
     int next_blocks, next_grid, prefetch_blocks;
+    int qvar;               // qgemm.cuh: hand-off variant / diagnostic switches (bit 0 set in production)
     GemmSeg seg[GEMM_MAX_SEG];
 };
 
