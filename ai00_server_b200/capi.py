@@ -94,6 +94,7 @@ SYMBOLS = [
 # debug build only (libb200rwkv_dbg.so): micro-benchmarks; the B200RWKV_* environment switches are honoured there
 DEBUG_SYMBOLS = [
     ("b200rwkv_debug_stream", C.c_int32, [C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+    ("b200rwkv_debug_mma_rate", C.c_int32, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     ("b200rwkv_debug_prefetch", C.c_int32, [C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.POINTER(C.c_float)]),
 ]
 DEBUG_LIB_PATH = os.path.join(_HERE, "libb200rwkv_dbg.so")

@@ -2849,6 +2849,24 @@ int32_t b200rwkv_debug_prefetch(int32_t device, double mbytes, int32_t consumers
     API_END
 }
 
+// tcgen05.mma rate of one instruction shape (streamtest.cuh): cycles[0] = issue loop, cycles[1] = until retired, for n MMAs.
+int32_t b200rwkv_debug_mma_rate(int32_t device, int32_t M, int32_t N, int32_t a_in_tmem, int32_t n, int64_t* cycles) {
+    API_BEGIN((b200rwkv_engine*)nullptr)
+    REQUIRE((M == 64 || M == 128) && N >= 16 && N <= 256 && N % 16 == 0 && n >= 1 && cycles, B200RWKV_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(device));
+    const size_t smem = 32768 + 65536 + 64;
+    CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DevTmp out(16);
+    for (int r = 0; r < 2; ++r) {          // first launch warms the instruction cache
+        mma_rate_kernel<<<1, 128, smem>>>(M, N, a_in_tmem, n, (long long*)out.p);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
+    long long h[2];
+    CK(cudaMemcpy(h, out.p, 16, cudaMemcpyDeviceToHost));
+    cycles[0] = h[0]; cycles[1] = h[1];
+    API_END
+}
 #endif   // B200RWKV_DEBUG
 
 // ---- exported SPMD entries: one rank, or all ranks of an in-process tensor-parallel engine at once ----

@@ -277,6 +277,9 @@ int32_t b200rwkv_debug_stream(int32_t device, int32_t kind, double gbytes, int32
                               float* ms_out);
 int32_t b200rwkv_debug_prefetch(int32_t device, double mbytes, int32_t consumers, int32_t pf_grid, int32_t skip, int32_t nblk,
                                 int32_t mode, double idle_us, int32_t reps, float* ms_out);
+/* SM cycles for n back-to-back tcgen05.mma kind::f16 of shape [M x 16] x [16 x N] on one SM, A operand from shared memory or
+ * tensor memory: cycles[0] = the issue loop, cycles[1] = until the last one has retired. */
+int32_t b200rwkv_debug_mma_rate(int32_t device, int32_t M, int32_t N, int32_t a_in_tmem, int32_t n, int64_t* cycles);
 #endif
 
 const char* b200rwkv_last_error(b200rwkv_engine*);
