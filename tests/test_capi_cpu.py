@@ -183,3 +183,24 @@ def test_read_state_host_only():
     with pytest.raises(capi.B200Error) as ei:           # a model without time_state is not a state file
         runtime.read_state(info, synth.make_st("tiny6", 0))
     assert ei.value.code == capi.ERR_INVALID
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The ctypes mirrors of the two ABI structs have the layout a C compiler gives include/b200rwkv.h (a plain C translation unit:
+    the header must stay C, not C++)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b200rwkv.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(b200rwkv_options), offsetof(b200rwkv_options, devices),\n'
+                   '  offsetof(b200rwkv_options, lora_st), offsetof(b200rwkv_options, quant_layers), sizeof(b200rwkv_info)); return 0; }\n')
+    exe = tmp_path / "sz"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    O = capi.Options
+    assert got == [C.sizeof(O), O.devices.offset, O.lora_st.offset, O.quant_layers.offset, C.sizeof(capi.Info)]
