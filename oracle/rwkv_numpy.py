@@ -23,9 +23,12 @@ reference's own call sites and on-disk contract:
   (x-fastest) == numpy C-order (L, N+2, C) (run.rs:987, lib.rs:267-272):
   row 0 = time-mix token shift, rows 1..N = WKV state, row N+1 = channel-mix
   token shift;
-* independent cross-checks committed under tests/golden/ (generated by
-  oracle/make_golden.py from flash-linear-attention's pure-torch naive
-  recurrences, which are present in this image).
+* independent cross-checks committed under tests/golden/: flash-linear-attention's
+  pure-torch naive recurrences (oracle/make_golden.py), its RWKV-6 / RWKV-7 layer
+  forwards and its whole `RWKV6ForCausalLM` / `RWKV7ForCausalLM` models on the tiny
+  synthetic weights (oracle/make_golden_fla_layers.py: logits 4e-7 from this file's).
+  fla is a third-party implementation of the published architecture, not the
+  reference's arithmetic, so the "unpinned" statement above stands.
 
 Math follows BlinkDL's published inference code (rwkv pip `model.py`
 att_one_v5_2/att_one_v6_0/ffn_one_v6 and RWKV-LM `rwkv_v7_demo_rnn.py`), as
