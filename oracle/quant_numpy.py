@@ -30,7 +30,7 @@ INT8_BLOCK = 128
 NF4_BLOCK = 64
 QUANT_NONE, QUANT_INT8, QUANT_NF4 = 0, 1, 2
 
-# bitsandbytes / QLoRA NormalFloat4 levels
+# bitsandbytes / QLoRA NormalFloat4 levels (normalised N(0,1) quantiles; tests/test_quant_cpu.py re-derives them from the published construction)
 NF4_LEVELS = np.array([
     -1.0, -0.6961928009986877, -0.5250730514526367, -0.39491748809814453, -0.28444138169288635, -0.18477343022823334,
     -0.09105003625154495, 0.0, 0.07958029955625534, 0.16093020141124725, 0.24611230194568634, 0.33791524171829224,

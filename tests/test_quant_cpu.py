@@ -75,6 +75,15 @@ def test_nf4_level_table_is_the_normalfloat_quantile_table():
     assert lv.shape == (16,) and lv[0] == -1 and lv[7] == 0 and lv[15] == 1 and (np.diff(lv) > 0).all()
     # asymmetric by construction: 8 levels on the positive side, 7 on the negative
     assert (lv > 0).sum() == 8 and (lv < 0).sum() == 7
+    # the published construction (QLoRA, Dettmers et al. 2023, App. E / bitsandbytes `create_normal_map(offset=0.9677083)`):
+    # 8 quantiles of N(0, 1) on the positive side, 7 on the negative, an exact zero, normalised to [-1, 1]
+    from scipy.stats import norm
+    offset = 0.9677083
+    pos = norm.ppf(np.linspace(offset, 0.5, 9)[:-1])
+    neg = -norm.ppf(np.linspace(offset, 0.5, 8)[:-1])
+    v = np.sort(np.concatenate([pos, [0.0], neg]))
+    v /= v.max()
+    assert np.abs(v - lv).max() < 1e-6
 
 
 def test_quantize_model_touches_only_projection_matrices_of_the_first_layers():
