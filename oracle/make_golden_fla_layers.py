@@ -341,12 +341,29 @@ def gen_models():
                                                                         eps6).reshape(x.shape)
                 blk.attn.gate_fn = F.silu
         with torch.no_grad():
-            logits = model(input_ids=torch.tensor([TOKENS]), use_cache=False).logits[0].numpy()
+            out = model(input_ids=torch.tensor([TOKENS]), use_cache=True)
+        logits = out.logits[0].numpy()
         orc = O.Oracle(w, "f32")
-        want, _ = orc.run(TOKENS, orc.state_init(), full=True)
+        want, want_state = orc.run(TOKENS, orc.state_init(), full=True)
         err = float(np.abs(logits - want).max() / np.abs(want).max())
         print(f"v{ver} {preset}: fla ForCausalLM logits vs oracle {err:.2e}, argmax equal {bool((logits.argmax(1) == want.argmax(1)).all())}")
-        np.savez_compressed(os.path.join(GOLD, f"model{ver}_fla.npz"), tokens=np.asarray(TOKENS, np.int64), logits=logits.astype(np.float32))
+        # the recurrent state fla's cache holds after the run, per layer: token-shift rows of both sub-layers and the WKV state as
+        # S[head][key][value] (fla keeps [K, V] for both versions; the oracle's RWKV-7 state is [value][key])
+        N = C // H
+        rec = {"tokens": np.asarray(TOKENS, np.int64), "logits": logits.astype(np.float32)}
+        worst = 0.0
+        for l in range(L):
+            st = out.past_key_values[l]
+            S = st["recurrent_state"][0].numpy().astype(np.float32)                      # [H, K, V]
+            rec[f"att_shift_{l}"] = st["conv_state"].reshape(-1).numpy().astype(np.float32)
+            rec[f"ffn_shift_{l}"] = st["ffn_state"].reshape(-1).numpy().astype(np.float32)
+            rec[f"wkv_kv_{l}"] = S
+            o_s = want_state[l, 1:1 + N].reshape(N, H, N).transpose(1, 0, 2)             # oracle rows: [head][i][j]
+            o_kv = o_s if ver == 6 else o_s.transpose(0, 2, 1)
+            worst = max(worst, float(np.abs(S - o_kv).max() / np.abs(o_kv).max()),
+                        float(np.abs(rec[f"att_shift_{l}"] - want_state[l, 0]).max()), float(np.abs(rec[f"ffn_shift_{l}"] - want_state[l, N + 1]).max()))
+        print(f"v{ver} {preset}: fla cache (shift rows, WKV state) vs oracle state, worst {worst:.2e}")
+        np.savez_compressed(os.path.join(GOLD, f"model{ver}_fla.npz"), **rec)
 
 
 if __name__ == "__main__":
