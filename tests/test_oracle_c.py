@@ -46,3 +46,16 @@ def test_c_oracle_matches_goldens(golden_dir, preset):
     got = np.stack(rows)
     assert np.abs(got - g["logits_f16"]).max() <= 1e-3 * np.abs(g["logits_f16"]).max()
     assert (got.argmax(1) == g["logits_f16"].argmax(1)).all()
+
+
+@pytest.mark.parametrize("preset,fixture", [("tiny6", "model6_fla.npz"), ("tiny7", "model7_fla.npz")])
+def test_c_oracle_matches_fla_causal_lm_fixture(golden_dir, preset, fixture):
+    """The C restatement (the CPU arm the bench times and the checker of the full-size GPU tests) against the logits of
+    flash-linear-attention's whole models on the same weights (oracle/make_golden_fla_layers.py)."""
+    g = np.load(os.path.join(golden_dir, fixture))
+    w = O.parse_st(synth.make_st(preset, 0))
+    rc = ref_c.RefC(w, "f32")
+    st = rc.state_init(1)
+    got = np.stack([rc.decode_step([int(t)], st)[0] for t in g["tokens"]])
+    assert np.abs(got - g["logits"]).max() <= 2e-5 * np.abs(g["logits"]).max()
+    assert (got.argmax(1) == g["logits"].argmax(1)).all()
