@@ -204,3 +204,53 @@ def test_ctypes_structs_match_the_header(tmp_path):
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     O = capi.Options
     assert got == [C.sizeof(O), O.devices.offset, O.lora_st.offset, O.quant_layers.offset, C.sizeof(capi.Info)]
+
+
+def test_c_host_program_links_and_calls_the_library(tmp_path):
+    """A plain C host (no Python, no torch) includes include/b200rwkv.h, links libb200rwkv.so and calls the host-only entry
+    points the Rust shim would call first (`Loader::info`, then `create`, which must fail loudly on a box without a GPU)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "ai00_server_b200")
+    st = synth.make_st("tiny7", 0)
+    stp = tmp_path / "m.st"
+    stp.write_bytes(st.tobytes())
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include "b200rwkv.h"
+int main(int argc, char** argv) {
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) return 2;
+    fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+    uint8_t* buf = (uint8_t*)malloc((size_t)n);
+    if (fread(buf, 1, (size_t)n, f) != (size_t)n) return 3;
+    b200rwkv_info info;
+    int32_t rc = b200rwkv_info_from_st(buf, (size_t)n, &info);
+    printf("%d %d %d %d %d %d %d %d\n", rc, info.version, info.num_layer, info.num_emb, info.num_hidden, info.num_vocab, info.num_head, info.head_size);
+    b200rwkv_engine* e = NULL;
+    rc = b200rwkv_create(buf, (size_t)n, 0, 2, 32, 0, &e);
+    printf("%d %s\n", rc, b200rwkv_last_error(NULL));
+    if (e) b200rwkv_destroy(e);
+    return 0;
+}
+''')
+    exe = tmp_path / "host"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", libdir, "-lb200rwkv",
+                    "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe), str(stp)], check=True, capture_output=True, text=True).stdout.splitlines()
+    s = synth.PRESETS["tiny7"]
+    assert [int(x) for x in out[0].split()] == [0, 7, s.L, s.C, s.F, s.V, s.H, s.N]
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        rc, msg = out[1].split(" ", 1)
+        assert int(rc) < 0 and "CUDA" in msg
